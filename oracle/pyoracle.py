@@ -1,0 +1,152 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) and of oracle/_ref.
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / `--impl reference` legs; never by allocnet_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+EVAL_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, _dp, _dp, C.c_int)
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (always possible: g++ only) and, when /root/reference is present, _ref."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "minco_oracle.hpp", "lbfgs_oracle.hpp")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    ref_missing = (not os.path.exists(os.path.join(_HERE, "_ref", "libref_lbfgs.so"))
+                   or not os.path.exists(os.path.join(_HERE, "liboracle_strict.so")))
+    if stale or ref_missing:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+
+
+def _ptr(a, typ=_dp):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Oracle:
+    def __init__(self, strict: bool = False):
+        """strict=True loads the -ffp-contract=off build (bit-comparable with oracle/_ref)."""
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "liboracle_strict.so" if strict else "liboracle.so"))
+        L = self.lib
+        L.orc_cost_create.restype = C.c_void_p
+        L.orc_cost_thunk_address.restype = C.c_void_p
+        L.orc_cost_thunk.restype = C.c_double
+        L.orc_forward_t.restype = L.orc_backward_t.restype = L.orc_backward_grad_t.restype = C.c_double
+        L.orc_forward_t.argtypes = [C.c_double]
+        L.orc_backward_t.argtypes = [C.c_double]
+        L.orc_backward_grad_t.argtypes = [C.c_double, C.c_double]
+        L.orc_smoothed_l1.argtypes = [C.c_double, C.c_double, _dp, _dp]
+        L.orc_cost_destroy.argtypes = [C.c_void_p]
+        L.orc_cost_thunk.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+        L.orc_cost_flat.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.orc_lbfgs_optimize.argtypes = [C.c_int, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip]
+        self.ref = None
+        ref_so = os.path.join(_HERE, "_ref", "libref_lbfgs.so")
+        if os.path.exists(ref_so):
+            self.ref = C.CDLL(ref_so)
+            self.ref.ref_lbfgs_optimize.argtypes = [C.c_int, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip]
+            self.ref.ref_lbfgs_strerror.restype = C.c_char_p
+
+    # ---- MINCO pieces ------------------------------------------------------
+    def minco_forward(self, S, head, tail, inPs, ts):
+        """-> dict(coeffs [2S*N][3], energy, gdC [2S*N][3], gdT [N], flat [N][3][2S])."""
+        ts = _f64(ts); N = ts.shape[0]
+        head, tail, inPs = _f64(head), _f64(tail), _f64(inPs if N > 1 else np.zeros((1, 3)))
+        coeffs = np.zeros((2 * S * N, 3)); gdC = np.zeros((2 * S * N, 3)); gdT = np.zeros(N)
+        flat = np.zeros((N, 3, 2 * S)); e = C.c_double(0.0)
+        rc = self.lib.orc_minco_forward(S, N, _ptr(head), _ptr(tail), _ptr(inPs), _ptr(ts), _ptr(coeffs),
+                                        C.byref(e), _ptr(gdC), _ptr(gdT), _ptr(flat))
+        assert rc == 0
+        return dict(coeffs=coeffs, energy=e.value, gdC=gdC, gdT=gdT, flat=flat)
+
+    def minco_propagate(self, S, head, tail, inPs, ts, gdC, gdT):
+        ts = _f64(ts); N = ts.shape[0]
+        head, tail, inPs = _f64(head), _f64(tail), _f64(inPs if N > 1 else np.zeros((1, 3)))
+        gdC, gdT = _f64(gdC), _f64(gdT)
+        gq = np.zeros((max(N - 1, 1), 3)); gT = np.zeros(N)
+        rc = self.lib.orc_minco_propagate(S, N, _ptr(head), _ptr(tail), _ptr(inPs), _ptr(ts), _ptr(gdC),
+                                          _ptr(gdT), _ptr(gq), _ptr(gT))
+        assert rc == 0
+        return gq[: N - 1], gT
+
+    def banded_solve(self, dense, p, q, b, adj=False):
+        dense = _f64(dense); b = _f64(b).copy()
+        n = dense.shape[0]; m = b.shape[1]
+        self.lib.orc_banded_solve(n, p, q, _ptr(dense), _ptr(b), m, int(adj))
+        return b
+
+    def smoothed_l1(self, mu, x):
+        f, df = C.c_double(0.0), C.c_double(0.0)
+        hit = self.lib.orc_smoothed_l1(mu, x, C.byref(f), C.byref(df))
+        return bool(hit), f.value, df.value
+
+    # ---- batched cost / optimize ------------------------------------------
+    def cost_batch(self, params, pb, x, nthreads=1):
+        """f [B], g [B][n] of the cost functional at x (CPU, fp64)."""
+        x = _f64(x); B, n = x.shape
+        f = np.zeros(B); g = np.zeros((B, n))
+        hp = pb.hpolys if pb.K > 0 else None
+        rc = self.lib.orc_cost_batch(C.byref(params), B, pb.N, _ptr(pb.head), _ptr(pb.tail), _ptr(hp),
+                                     _ptr(pb.hrows, _ip), pb.K, _ptr(x), _ptr(f), _ptr(g), nthreads)
+        assert rc == 0
+        return f, g
+
+    def optimize_batch(self, params, pb, x0=None, nthreads=1):
+        x = _f64(pb.x0() if x0 is None else x0).copy(); B, n = x.shape
+        S, N = params.S, pb.N
+        f = np.zeros(B); status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32)
+        evals = np.zeros(B, np.int32); coeffs = np.zeros((B, N, 3, 2 * S)); T = np.zeros((B, N))
+        hp = pb.hpolys if pb.K > 0 else None
+        rc = self.lib.orc_optimize_batch(C.byref(params), B, N, _ptr(pb.head), _ptr(pb.tail), _ptr(hp),
+                                         _ptr(pb.hrows, _ip), pb.K, _ptr(x), _ptr(f), _ptr(status, _ip),
+                                         _ptr(iters, _ip), _ptr(evals, _ip), _ptr(coeffs), _ptr(T), nthreads)
+        assert rc == 0
+        return dict(x=x, f=f, status=status, iters=iters, evals=evals, coeffs=coeffs, T=T)
+
+    def hardware_threads(self):
+        return int(self.lib.orc_hardware_threads())
+
+    # ---- single-problem cost instance (lbfgs callback ABI) -------------------
+    def cost_instance(self, params, pb, b):
+        one = pb.slice(b, b + 1)
+        hp = one.hpolys if one.K > 0 else None
+        inst = self.lib.orc_cost_create(C.byref(params), one.N, _ptr(one.head), _ptr(one.tail), _ptr(hp),
+                                        _ptr(one.hrows, _ip), one.K)
+        return _CostInstance(self, inst, one)
+
+    def lbfgs(self, n, x0, eval_ptr, inst, params, which="oracle"):
+        """Run the restated ('oracle') or the verbatim reference ('ref') L-BFGS on a raw C callback."""
+        x = _f64(x0).copy(); f = C.c_double(0.0); it = C.c_int(0); ev = C.c_int(0)
+        fn = self.lib.orc_lbfgs_optimize if which == "oracle" else self.ref.ref_lbfgs_optimize
+        ret = fn(n, _ptr(x), C.byref(f), eval_ptr, inst, C.cast(C.byref(params), C.c_void_p), C.byref(it), C.byref(ev))
+        return dict(x=x, f=f.value, ret=int(ret), iters=it.value, evals=ev.value)
+
+
+class _CostInstance:
+    def __init__(self, orc, inst, one):
+        self.orc, self.inst, self._keep = orc, inst, one
+        self.thunk = orc.lib.orc_cost_thunk_address()
+
+    def __call__(self, x):
+        x = _f64(x); g = np.zeros_like(x)
+        f = self.orc.lib.orc_cost_thunk(self.inst, _ptr(x), _ptr(g), x.shape[0])
+        return f, g
+
+    def close(self):
+        if self.inst:
+            self.orc.lib.orc_cost_destroy(self.inst)
+            self.inst = None

@@ -1,0 +1,271 @@
+"""Pins for the MINCO / cost-functional part of the CPU oracle (oracle/minco_oracle.hpp).
+
+The reference has no MINCO source and no tests for this path, so the
+oracle is pinned by independent restatements written here:
+  (1) banded LU / solve / solveAdj vs numpy dense solves,
+  (2) explicit S=3 rows typed from SURVEY.md Appendix A.2 vs the oracle's general-S rule,
+  (3) KKT of the REFERENCE QP formulation (Q of planner/qp_solver.hpp:223-234, boundary rows
+      :148-160, continuity rows :163-177, flatten idx :133) reproduces the MINCO coefficients,
+  (4) E == 2 * Trajectory<5>::getTrajCost(3) (gcopter/trajectory.hpp:396-420 constants),
+  (5) finite differences on propogateGrad and on the whole cost functional,
+  (6) smoothedL1 (gcopter/firi.hpp:60-84) and the tau<->T map properties,
+  (7) an mpmath 40-digit solve on a few seeds.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from allocnet_b200 import synth
+from allocnet_b200.params import default_params, energy_only
+
+
+def fact(d):
+    return float(math.factorial(d))
+
+
+def beta(t, d, D):
+    out = np.zeros(D)
+    for k in range(d, D):
+        out[k] = fact(k) / fact(k - d) * t ** (k - d)
+    return out
+
+
+def dense_minco(S, head, tail, q, T):
+    """Independent dense build of A, b by the general rule of SURVEY.md Appendix A.2."""
+    D, N = 2 * S, len(T)
+    A = np.zeros((D * N, D * N)); b = np.zeros((D * N, 3))
+    for d in range(S):
+        A[d, d] = fact(d); b[d] = head[d]
+    for i in range(N - 1):
+        r, c0 = D * i + S, D * i
+        for j in range(S - 1):
+            d = S + j
+            A[r + j, c0:c0 + D] = beta(T[i], d, D); A[r + j, c0 + D + d] = -fact(d)
+        A[r + S - 1, c0:c0 + D] = beta(T[i], 0, D); b[r + S - 1] = q[i]
+        for d in range(S):
+            A[r + S + d, c0:c0 + D] = beta(T[i], d, D); A[r + S + d, c0 + D + d] = -fact(d)
+    for d in range(S):
+        A[D * N - S + d, D * (N - 1):] = beta(T[N - 1], d, D); b[D * N - S + d] = tail[d]
+    return A, b
+
+
+def rand_problem(rng, S, N):
+    head = rng.normal(size=(S, 3)); tail = rng.normal(size=(S, 3))
+    q = np.cumsum(rng.normal(size=(max(N - 1, 0), 3)), axis=0)
+    T = rng.uniform(0.6, 2.0, size=N)
+    return head, tail, q, T
+
+
+def test_banded_matches_dense(oracle):
+    rng = np.random.default_rng(1)
+    for n, p, q in [(12, 3, 2), (48, 6, 6), (64, 8, 8), (5, 1, 1)]:
+        A = np.zeros((n, n))
+        for i in range(n):
+            for j in range(max(0, i - p), min(n, i + q + 1)):
+                A[i, j] = rng.normal()
+            A[i, i] += 6.0
+        b = rng.normal(size=(n, 3))
+        np.testing.assert_allclose(oracle.banded_solve(A, p, q, b), np.linalg.solve(A, b), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(oracle.banded_solve(A, p, q, b, adj=True), np.linalg.solve(A.T, b), rtol=0, atol=1e-12)
+
+
+def test_s3_rows_typed_from_appendix_a2():
+    """The general-S rule must produce exactly the S=3 entries listed in SURVEY.md Appendix A.2."""
+    rng = np.random.default_rng(2)
+    head, tail, q, T = rand_problem(rng, 3, 4)
+    A, b = dense_minco(3, head, tail, q, T)
+    t = T[1]; r = 6
+    T1, T2, T3, T4, T5 = t, t**2, t**3, t**4, t**5
+    exp = np.zeros((6, 24))
+    exp[0, r + 3], exp[0, r + 4], exp[0, r + 5], exp[0, r + 9] = 6, 24 * T1, 60 * T2, -6
+    exp[1, r + 4], exp[1, r + 5], exp[1, r + 10] = 24, 120 * T1, -24
+    exp[2, r:r + 6] = [1, T1, T2, T3, T4, T5]
+    exp[3, r:r + 6] = [1, T1, T2, T3, T4, T5]; exp[3, r + 6] = -1
+    exp[4, r + 1:r + 6] = [1, 2 * T1, 3 * T2, 4 * T3, 5 * T4]; exp[4, r + 7] = -1
+    exp[5, r + 2:r + 6] = [2, 6 * T1, 12 * T2, 20 * T3]; exp[5, r + 8] = -2
+    np.testing.assert_allclose(A[r + 3:r + 9], exp, rtol=1e-15)
+    assert A[0, 0] == 1 and A[1, 1] == 1 and A[2, 2] == 2
+    np.testing.assert_array_equal(b[r + 5], q[1])
+
+
+@pytest.mark.parametrize("S,N", [(3, 1), (3, 2), (3, 5), (3, 8), (3, 16), (4, 2), (4, 8), (4, 16)])
+def test_coefficients_match_dense_solve(oracle, S, N):
+    rng = np.random.default_rng(10 * S + N)
+    head, tail, q, T = rand_problem(rng, S, N)
+    out = oracle.minco_forward(S, head, tail, q, T)
+    A, b = dense_minco(S, head, tail, q, T)
+    c = np.linalg.solve(A, b)
+    np.testing.assert_allclose(out["coeffs"], c, rtol=0, atol=2e-9 * max(1.0, np.abs(c).max()))
+    # band half-width is 2S
+    ii, jj = np.nonzero(A)
+    assert np.max(np.abs(ii - jj)) <= 2 * S
+    # Trajectory packing: [piece][axis][k], k=0 highest power (trajectory.hpp:79-83)
+    D = 2 * S
+    for i in range(N):
+        for a in range(3):
+            np.testing.assert_array_equal(out["flat"][i, a], out["coeffs"][D * i:D * i + D, a][::-1])
+
+
+def test_energy_s3_explicit_and_trajcost_identity(oracle):
+    rng = np.random.default_rng(3)
+    head, tail, q, T = rand_problem(rng, 3, 5)
+    out = oracle.minco_forward(3, head, tail, q, T)
+    c = out["coeffs"].reshape(5, 6, 3)
+    E = 0.0; half = 0.0
+    for i in range(5):
+        t = T[i]; c3, c4, c5 = c[i, 3], c[i, 4], c[i, 5]
+        E += (36 * c3 @ c3 * t + 144 * c4 @ c3 * t**2 + 192 * c4 @ c4 * t**3 + 240 * c5 @ c3 * t**3
+              + 720 * c5 @ c4 * t**4 + 720 * c5 @ c5 * t**5)
+        # Trajectory<5>::getTrajCost(3): 0.5 z^T Q z, z = leading 3 (descending) coeffs; trajectory.hpp:396-420
+        Q = np.array([[720 * t**5, 360 * t**4, 120 * t**3], [360 * t**4, 192 * t**3, 72 * t**2],
+                      [120 * t**3, 72 * t**2, 36 * t]])
+        for a in range(3):
+            z = out["flat"][i, a, :3]
+            half += 0.5 * z @ Q @ z
+    assert out["energy"] == pytest.approx(E, rel=1e-13)
+    assert out["energy"] == pytest.approx(2.0 * half, rel=1e-13)
+
+
+def test_kkt_of_reference_qp_reproduces_minco(oracle):
+    """Reference QP (equality part) + waypoint rows == MINCO optimum; layouts of qp_solver.hpp."""
+    rng = np.random.default_rng(4)
+    S, N, d = 3, 5, 6
+    head, tail, q, T = rand_problem(rng, S, N)
+    nv = N * 3 * d
+
+    def t_state(t):  # get_t_state, qp_solver.hpp:90-116 (descending powers)
+        return np.array([[t**5, t**4, t**3, t**2, t, 1], [5 * t**4, 4 * t**3, 3 * t**2, 2 * t, 1, 0],
+                         [20 * t**3, 12 * t**2, 6 * t, 2, 0, 0]])
+    zero_A = np.zeros((3, 6)); zero_A[0, 5] = 1; zero_A[1, 4] = 1; zero_A[2, 3] = 2  # setOrder :76-78
+    rows, rhs = [], []
+    for a in range(3):  # boundary :148-160
+        for k in range(3):
+            r = np.zeros(nv); r[a * d:a * d + d] = zero_A[k]; rows.append(r); rhs.append(head[k, a])
+        for k in range(3):
+            r = np.zeros(nv); r[(N - 1) * 3 * d + a * d:(N - 1) * 3 * d + a * d + d] = t_state(T[N - 1])[k]
+            rows.append(r); rhs.append(tail[k, a])
+    for i in range(N - 1):  # continuity :163-177
+        for a in range(3):
+            col = i * 3 * d + a * d
+            for k in range(3):
+                r = np.zeros(nv); r[col:col + d] = t_state(T[i])[k]; r[col + 3 * d:col + 3 * d + d] = -zero_A[k]
+                rows.append(r); rhs.append(0.0)
+            r = np.zeros(nv); r[col + 3 * d:col + 3 * d + d] = zero_A[0]; rows.append(r); rhs.append(q[i, a])  # waypoint
+    Aeq = np.array(rows); beq = np.array(rhs)
+    Q = np.zeros((nv, nv))
+    for i in range(N):  # :223-234
+        t = T[i]
+        cq = np.array([[720 * t**5, 360 * t**4, 120 * t**3], [360 * t**4, 192 * t**3, 72 * t**2],
+                       [120 * t**3, 72 * t**2, 36 * t]])
+        for a in range(3):
+            col = i * 3 * d + a * d
+            Q[col:col + 3, col:col + 3] = cq
+    m = Aeq.shape[0]
+    KKT = np.block([[Q, Aeq.T], [Aeq, np.zeros((m, m))]])
+    z = np.linalg.lstsq(KKT, np.concatenate([np.zeros(nv), beq]), rcond=None)[0][:nv]
+    out = oracle.minco_forward(S, head, tail, q, T)
+    np.testing.assert_allclose(out["flat"].reshape(-1), z, rtol=0, atol=1e-7 * np.abs(z).max())
+    assert 0.5 * z @ Q @ z == pytest.approx(out["energy"] / 2.0, rel=1e-8)
+
+
+@pytest.mark.parametrize("S,N", [(3, 2), (3, 5), (3, 8), (4, 8), (3, 16)])
+def test_propagate_grad_finite_differences(oracle, S, N):
+    rng = np.random.default_rng(100 + S * 17 + N)
+    head, tail, q, T = rand_problem(rng, S, N)
+    W = rng.normal(size=(2 * S * N, 3))  # J = E + <W, c>
+
+    def J(qq, TT):
+        o = oracle.minco_forward(S, head, tail, qq, TT)
+        return o["energy"] + np.sum(W * o["coeffs"])
+    o = oracle.minco_forward(S, head, tail, q, T)
+    gq, gT = oracle.minco_propagate(S, head, tail, q, T, o["gdC"] + W, o["gdT"])
+    h = 1e-4  # 5-point stencil: truncation O(h^4), round-off ~ eps*|J|*cond/h
+
+    def fd5(fun):
+        return (8.0 * (fun(h) - fun(-h)) - (fun(2 * h) - fun(-2 * h))) / (12.0 * h)
+    for i in range(N):
+        def along(e, i=i):
+            TT = T.copy(); TT[i] += e
+            return J(q, TT)
+        fd = fd5(along)
+        assert gT[i] == pytest.approx(fd, rel=5e-6, abs=5e-6 * max(1.0, np.abs(gT).max()))
+    for i in range(N - 1):
+        for a in range(3):
+            def along(e, i=i, a=a):
+                qq = q.copy(); qq[i, a] += e
+                return J(qq, T)
+            fd = fd5(along)
+            assert gq[i, a] == pytest.approx(fd, rel=5e-6, abs=5e-6 * max(1.0, np.abs(gq).max()))
+
+
+@pytest.mark.parametrize("S,N,K", [(3, 5, 16), (3, 8, 16), (4, 8, 16), (3, 8, 0)])
+def test_cost_functional_finite_differences(oracle, S, N, K):
+    p = default_params(S)
+    if K == 0:
+        p = energy_only(p)
+    pb = synth.make_problems(3, N, K, S, time_scale=0.8)  # short times: many active hinges
+    x = pb.x0()
+    for b in range(pb.B):
+        ci = oracle.cost_instance(p, pb, b)
+        f0, g0 = ci(x[b])
+        h = 1e-7
+        scale = max(1.0, np.abs(g0).max())
+        for i in range(x.shape[1]):
+            xp = x[b].copy(); xp[i] += h; xm = x[b].copy(); xm[i] -= h
+            fd = (ci(xp)[0] - ci(xm)[0]) / (2 * h)
+            assert abs(fd - g0[i]) <= 5e-6 * scale, (b, i, fd, g0[i])
+        ci.close()
+
+
+def test_smoothed_l1_and_time_map(oracle):
+    mu = 1e-2
+    assert oracle.smoothed_l1(mu, -1e-3) == (False, 0.0, 0.0)
+    hit, f, df = oracle.smoothed_l1(mu, 0.5)
+    assert hit and f == pytest.approx(0.5 - 0.5 * mu) and df == 1.0
+    hit, f, df = oracle.smoothed_l1(mu, 0.5 * mu)   # (mu - x/2)(x/mu)^3
+    assert hit and f == pytest.approx((mu - 0.25 * mu) * 0.125) and df == pytest.approx(0.25 * (-0.25 + 3 * 0.75))
+    # C1 at x = mu
+    _, f1, d1 = oracle.smoothed_l1(mu, mu * (1 - 1e-9)); _, f2, d2 = oracle.smoothed_l1(mu, mu * (1 + 1e-9))
+    assert f1 == pytest.approx(f2, abs=1e-10) and d1 == pytest.approx(d2, abs=1e-7)
+    L = oracle.lib
+    for tau in [-3.0, -0.5, 0.0, 0.3, 2.5]:
+        T = L.orc_forward_t(tau)
+        assert T > 0 and L.orc_backward_t(T) == pytest.approx(tau, abs=1e-12)
+        h = 1e-6
+        fd = (L.orc_forward_t(tau + h) - L.orc_forward_t(tau - h)) / (2 * h)
+        assert L.orc_backward_grad_t(tau, 1.0) == pytest.approx(fd, rel=1e-8)
+    np.testing.assert_allclose(synth.forward_t(synth.backward_t(np.array([0.2, 1.0, 3.0]))), [0.2, 1.0, 3.0], rtol=1e-14)
+
+
+def test_mpmath_certifies_fp64_oracle(oracle):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(7)
+    for S, N in [(3, 8), (4, 5)]:
+        head, tail, q, T = rand_problem(rng, S, N)
+        A, b = dense_minco(S, head, tail, q, T)  # entries are exact products/powers of doubles up to 1 ulp
+        D = 2 * S
+        Am = mp.matrix(D * N, D * N)
+        for d in range(S):
+            Am[d, d] = mp.factorial(d)
+        def mbeta(t, d):
+            return [mp.factorial(k) / mp.factorial(k - d) * mp.mpf(t) ** (k - d) if k >= d else mp.mpf(0) for k in range(D)]
+        for i in range(N - 1):
+            r, c0 = D * i + S, D * i
+            for j in range(S - 1):
+                d = S + j
+                for k, v in enumerate(mbeta(T[i], d)): Am[r + j, c0 + k] = v
+                Am[r + j, c0 + D + d] = -mp.factorial(d)
+            for k, v in enumerate(mbeta(T[i], 0)): Am[r + S - 1, c0 + k] = v
+            for d in range(S):
+                for k, v in enumerate(mbeta(T[i], d)): Am[r + S + d, c0 + k] = v
+                Am[r + S + d, c0 + D + d] = -mp.factorial(d)
+        for d in range(S):
+            for k, v in enumerate(mbeta(T[N - 1], d)): Am[D * N - S + d, D * (N - 1) + k] = v
+        c = np.zeros((D * N, 3))
+        for a in range(3):
+            col = mp.lu_solve(Am, mp.matrix(b[:, a].tolist()))
+            c[:, a] = [float(col[i]) for i in range(D * N)]
+        out = oracle.minco_forward(S, head, tail, q, T)
+        assert np.max(np.abs(out["coeffs"] - c)) <= 1e-10 * max(1.0, np.abs(c).max())
