@@ -1,0 +1,239 @@
+"""Host-side binding of the C-ABI in include/mincob.h (allocnet_b200/libmincob.so).
+
+This is the Python mirror of the reference-side interface for the trajectory back-end slot
+(`qp_solver.solve(...)` at src/planner/include/planner/learning_planner.hpp:196 and the
+`lbfgs_optimize` / `lbfgs_evaluate_t` ABI of src/planner/include/gcopter/lbfgs.hpp:200-202,434-440),
+batched over B problems.  Method names follow the upstream MINCO / GCOPTER API restated in
+SURVEY.md Appendix A/B (setParameters, getEnergy, propogateGrad, costFunctional, optimize).
+
+There is no CPU fallback: if the CUDA library is missing, or no device is present, the calls
+raise.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import MincobParams, default_params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmincob.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+SYMBOLS = [
+    "mincob_version", "mincob_default_params", "mincob_create", "mincob_destroy", "mincob_set_params",
+    "mincob_set_stream", "mincob_synchronize", "mincob_last_error", "mincob_strerror", "mincob_lbfgs_strerror",
+    "mincob_set_problems", "mincob_set_problems_device", "mincob_evaluate", "mincob_evaluate_device",
+    "mincob_optimize", "mincob_optimize_device", "mincob_last_kernel_ms", "mincob_minco_forward",
+    "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
+    "mincob_comm_destroy",
+]
+
+
+class MincobError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libmincob.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MincobError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.mincob_last_error.restype = C.c_char_p
+    L.mincob_strerror.restype = C.c_char_p
+    L.mincob_lbfgs_strerror.restype = C.c_char_p
+    L.mincob_create.argtypes = [C.POINTER(_vp), C.POINTER(MincobParams), C.c_int]
+    L.mincob_destroy.argtypes = [_vp]
+    L.mincob_set_params.argtypes = [_vp, C.POINTER(MincobParams)]
+    L.mincob_set_stream.argtypes = [_vp, _vp]
+    L.mincob_synchronize.argtypes = [_vp]
+    L.mincob_last_error.argtypes = [_vp]
+    L.mincob_set_problems.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
+    L.mincob_set_problems_device.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
+    L.mincob_evaluate.argtypes = [_vp, _vp, _vp, _vp]
+    L.mincob_evaluate_device.argtypes = [_vp, _vp, _vp, _vp]
+    L.mincob_optimize.argtypes = [_vp] + [_vp] * 7
+    L.mincob_optimize_device.argtypes = [_vp] + [_vp] * 7
+    L.mincob_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.mincob_minco_forward.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 9
+    L.mincob_minco_propagate.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 8
+    L.mincob_nccl_unique_id.argtypes = [_vp]
+    L.mincob_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    L.mincob_allgather_device.argtypes = [_vp, _vp, _vp, C.c_int64]
+    L.mincob_comm_destroy.argtypes = [_vp]
+    _lib = L
+    return L
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor (contiguous) -> raw device pointer."""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise MincobError("device entry points need contiguous CUDA tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+class MincoBatch:
+    """Batched MINCO optimizer handle (one per GPU).  Mirrors GCOPTER_PolytopeSFC: setup -> optimize."""
+
+    def __init__(self, params: MincobParams | None = None, device: int = 0):
+        self.L = load_library()
+        self.params = params if params is not None else default_params()
+        self.h = _vp()
+        rc = self.L.mincob_create(C.byref(self.h), C.byref(self.params), int(device))
+        if rc != 0:
+            raise MincobError(f"mincob_create failed: {self.L.mincob_strerror(rc).decode()} (rc={rc})")
+        self.device = int(device)
+        self.B = self.N = self.K = 0
+        self._keep = None
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise MincobError(f"{self.L.mincob_strerror(rc).decode()}: {self.L.mincob_last_error(self.h).decode()} (rc={rc})")
+
+    def close(self):
+        if self.h:
+            self.L.mincob_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def S(self):
+        return int(self.params.S)
+
+    @property
+    def nvars(self):
+        return self.N + 3 * (self.N - 1)
+
+    def set_params(self, params: MincobParams):
+        self._check(self.L.mincob_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.L.mincob_set_stream(self.h, _vp(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self._check(self.L.mincob_synchronize(self.h))
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        self._check(self.L.mincob_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    # -- problems -------------------------------------------------------------------------
+    def set_problems(self, pb):
+        """pb: allocnet_b200.synth.ProblemBatch (host numpy arrays in the C-ABI layouts)."""
+        if pb.S != self.S:
+            raise MincobError(f"problem batch has S={pb.S}, handle has S={self.S}")
+        hp = pb.hpolys if pb.K > 0 else None
+        hr = pb.hrows if pb.K > 0 else None
+        self._check(self.L.mincob_set_problems(self.h, pb.B, pb.N, pb.K, _np_ptr(pb.head), _np_ptr(pb.tail),
+                                               _np_ptr(hp), _np_ptr(hr)))
+        self.B, self.N, self.K = pb.B, pb.N, pb.K
+
+    def set_problems_device(self, B, N, K, head, tail, hpolys=None, hrows=None):
+        self._check(self.L.mincob_set_problems_device(self.h, B, N, K, _dev_ptr(head), _dev_ptr(tail),
+                                                      _dev_ptr(hpolys), _dev_ptr(hrows)))
+        self.B, self.N, self.K = B, N, K
+        self._keep = (head, tail, hpolys, hrows)
+
+    # -- costFunctional ---------------------------------------------------------------------
+    def evaluate(self, x):
+        x = _f64(x)
+        if x.shape != (self.B, self.nvars):
+            raise MincobError(f"x must be [{self.B}][{self.nvars}]")
+        f = np.empty(self.B); g = np.empty_like(x)
+        self._check(self.L.mincob_evaluate(self.h, _np_ptr(x), _np_ptr(f), _np_ptr(g)))
+        return f, g
+
+    def evaluate_device(self, x, f, g):
+        self._check(self.L.mincob_evaluate_device(self.h, _dev_ptr(x), _dev_ptr(f), _dev_ptr(g)))
+
+    # -- lbfgs_optimize on costFunctional + getTrajectory -------------------------------------
+    def optimize(self, x0, want_coeffs=True):
+        x = _f64(x0).copy()
+        if x.shape != (self.B, self.nvars):
+            raise MincobError(f"x must be [{self.B}][{self.nvars}]")
+        B, N, S = self.B, self.N, self.S
+        f = np.zeros(B); status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32); evals = np.zeros(B, np.int32)
+        coeffs = np.zeros((B, N, 3, 2 * S)) if want_coeffs else None
+        T = np.zeros((B, N)) if want_coeffs else None
+        self._check(self.L.mincob_optimize(self.h, _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(iters),
+                                           _np_ptr(evals), _np_ptr(coeffs), _np_ptr(T)))
+        return dict(x=x, f=f, status=status, iters=iters, evals=evals, coeffs=coeffs, T=T)
+
+    def optimize_host_buffers(self, x, f, status, iters, evals, coeffs, T):
+        """In-place variant on caller-owned (e.g. pinned) host arrays; used by bench.py's e2e leg."""
+        self._check(self.L.mincob_optimize(self.h, _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(iters),
+                                           _np_ptr(evals), _np_ptr(coeffs), _np_ptr(T)))
+
+    def optimize_device(self, x, f=None, status=None, iters=None, evals=None, coeffs=None, T=None):
+        self._check(self.L.mincob_optimize_device(self.h, _dev_ptr(x), _dev_ptr(f), _dev_ptr(status), _dev_ptr(iters),
+                                                  _dev_ptr(evals), _dev_ptr(coeffs), _dev_ptr(T)))
+
+    # -- MINCO_S3NU / S4NU building blocks ---------------------------------------------------
+    def minco_forward(self, head, tail, inPs, ts):
+        """setParameters + getCoeffs/getEnergy/getEnergyPartialGradBy{Coeffs,Times}/getTrajectory for B problems."""
+        ts = _f64(ts); B, N = ts.shape; S = self.S
+        head, tail = _f64(head), _f64(tail)
+        inPs = _f64(inPs) if N > 1 else np.zeros((B, 1, 3))
+        coeffs = np.zeros((B, 2 * S * N, 3)); energy = np.zeros(B); gdC = np.zeros((B, 2 * S * N, 3))
+        gdT = np.zeros((B, N)); flat = np.zeros((B, N, 3, 2 * S))
+        self._check(self.L.mincob_minco_forward(self.h, B, N, _np_ptr(head), _np_ptr(tail), _np_ptr(inPs), _np_ptr(ts),
+                                                _np_ptr(coeffs), _np_ptr(energy), _np_ptr(gdC), _np_ptr(gdT), _np_ptr(flat)))
+        return dict(coeffs=coeffs, energy=energy, gdC=gdC, gdT=gdT, flat=flat)
+
+    def minco_propagate(self, head, tail, inPs, ts, gdC, gdT):
+        """propogateGrad (upstream spelling) for B problems -> gradByPoints [B][N-1][3], gradByTimes [B][N]."""
+        ts = _f64(ts); B, N = ts.shape
+        head, tail, gdC, gdT = _f64(head), _f64(tail), _f64(gdC), _f64(gdT)
+        inPs = _f64(inPs) if N > 1 else np.zeros((B, 1, 3))
+        gq = np.zeros((B, max(N - 1, 1), 3)); gT = np.zeros((B, N))
+        self._check(self.L.mincob_minco_propagate(self.h, B, N, _np_ptr(head), _np_ptr(tail), _np_ptr(inPs), _np_ptr(ts),
+                                                  _np_ptr(gdC), _np_ptr(gdT), _np_ptr(gq), _np_ptr(gT)))
+        return gq[:, : N - 1], gT
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.L.mincob_nccl_unique_id(buf)
+        if rc != 0:
+            raise MincobError(f"mincob_nccl_unique_id: {self.L.mincob_strerror(rc).decode()}")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.L.mincob_comm_init(self.h, nranks, rank, buf))
+
+    def allgather_device(self, send, recv, count_per_rank: int):
+        self._check(self.L.mincob_allgather_device(self.h, _dev_ptr(send), _dev_ptr(recv), int(count_per_rank)))
+
+
+def lbfgs_strerror(status: int) -> str:
+    return load_library().mincob_lbfgs_strerror(int(status)).decode()

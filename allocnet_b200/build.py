@@ -1,0 +1,73 @@
+"""In-tree build of allocnet_b200/libmincob.so (nvcc, sm_100a only).
+
+Six (S, LPT) kernel objects + the host API object are compiled in parallel and linked into one
+shared library next to this file, so it travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libmincob.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+INST = [(S, L) for S in (3, 4) for L in (8, 16, 32)]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libmincob.so cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "mincob.h")]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def _run(cmd, log):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(log, "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"build step failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return r.stderr
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = []
+    for S, L in INST:
+        o = os.path.join(OBJ, f"kernels_s{S}_l{L}.o")
+        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", "-c",
+                      os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
+    o = os.path.join(OBJ, "mincob.o")
+    jobs.append(([nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
+    if verbose:
+        for (cmd, o), out in zip(jobs, outs):
+            print(os.path.basename(o))
+            print("\n".join(l for l in out.splitlines() if "registers" in l or "spill" in l or "Compiling" in l))
+    _run([nvcc, *ARCH, "-shared", "-o", LIB, *[j[1] for j in jobs], "-ldl"], os.path.join(OBJ, "link.log"))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,65 @@
+// args.h -- plain argument blocks shared by the host API (mincob.cu) and the kernels.
+#pragma once
+namespace mincob {
+
+// reference codes, gcopter/lbfgs.hpp:135-184
+enum {
+    LBFGS_CONVERGENCE = 0,
+    LBFGS_STOP = 1,
+    LBFGS_CANCELED = 2,
+    LBFGSERR_UNKNOWNERROR = -1024,
+    LBFGSERR_INVALID_N,
+    LBFGSERR_INVALID_MEMSIZE,
+    LBFGSERR_INVALID_GEPSILON,
+    LBFGSERR_INVALID_TESTPERIOD,
+    LBFGSERR_INVALID_DELTA,
+    LBFGSERR_INVALID_MINSTEP,
+    LBFGSERR_INVALID_MAXSTEP,
+    LBFGSERR_INVALID_FDECCOEFF,
+    LBFGSERR_INVALID_SCURVCOEFF,
+    LBFGSERR_INVALID_MACHINEPREC,
+    LBFGSERR_INVALID_MAXLINESEARCH,
+    LBFGSERR_INVALID_FUNCVAL,
+    LBFGSERR_MINIMUMSTEP,
+    LBFGSERR_MAXIMUMSTEP,
+    LBFGSERR_MAXIMUMLINESEARCH,
+    LBFGSERR_MAXIMUMITERATION,
+    LBFGSERR_WIDTHTOOSMALL,
+    LBFGSERR_INVALIDPARAMETERS,
+    LBFGSERR_INCREASEGRADIENT,
+};
+
+struct DevParams {
+    int kappa;
+    double mu, w_pos, w_vel, w_acc, w_jerk, vmax2, amax2, jmax2, rho;
+    int penalties;  // 0: energy-only fast path (all weights zero)
+    // L-BFGS (gcopter/lbfgs.hpp:15-129)
+    int mem, past, max_iter, max_ls;
+    double g_eps, delta, min_step, max_step, f_dec, s_curv, cautious, mach_prec;
+};
+
+// one batch of problems in the C-ABI layouts of include/mincob.h
+struct BatchArgs {
+    int B, N, K;
+    const double *head, *tail, *hpolys;
+    const int *hrows;
+    // evaluate
+    const double *x_in;
+    double *f_out, *g_out;
+    // optimize
+    double *x, *coeffs, *T;
+    int *status, *iters, *evals;
+    int *counter;               // work queue head
+    unsigned long long *total_evals;  // optional: sum of evaluations (for the roofline numerator)
+};
+
+// MINCO building blocks (setParameters / getEnergy / ... / propogateGrad)
+struct MincoArgs {
+    int B, N;
+    const double *head, *tail, *inPs, *ts;
+    const double *gdC_in, *gdT_in;             // propagate
+    double *coeffs_asc, *energy, *gdC, *gdT, *flat;  // forward
+    double *gradByPoints, *gradByTimes;        // propagate
+};
+
+}  // namespace mincob

@@ -1,0 +1,656 @@
+// ============================================================================
+// minco_device.cuh -- device-side MINCO cost functional for sm_100a.
+//
+// One LANE per trajectory piece, LPT (8/16/32) lanes per trajectory, 32/LPT trajectories per
+// warp; all cross-piece traffic is warp shuffles inside the LPT-lane group, so groups of one
+// warp are independent (every shuffle names only its own group's lanes).
+//
+// What is computed (same call sequence as the upstream GCOPTER costFunctional restated in
+// SURVEY.md Appendix B.1; NOT in /root/reference):
+//   forwardT -> MINCO setParameters (banded solve, Appendix A.2) -> getEnergy +
+//   getEnergyPartialGradBy{Coeffs,Times} (A.3) -> attachPenaltyFunctional (B.2, smoothedL1 of
+//   gcopter/firi.hpp:60-84) -> propogateGrad (A.4) -> + rho*sum(T) -> backwardGradT.
+//
+// How the banded solve is done here.  The 2S*N x 2S*N band of minco.hpp is a 48-step serial
+// elimination for N=8.  Its rows say "the spline is C^(2S-2) at the waypoints", which is the
+// stationarity of E = sum_i int |p_i^(S)|^2 with respect to the junction derivatives
+// y_j = (p',..,p^(S-1))(t_j).  In Hermite form c_i = H(T_i) s_i, s_i = [start state; end state],
+//   E = sum_i s_i^T W(T_i) s_i,  W(T) = T^(1-2S) L What L,  L = diag(1,T,..,T^(S-1)) twice,
+// so y solves a symmetric positive definite BLOCK-TRIDIAGONAL system with (S-1)x(S-1) blocks
+// and one block row per junction.  Lane j builds block row j from T_{j-1}, T_j and the system is
+// solved by parallel cyclic reduction: log2(LPT) shuffle rounds instead of 2S*N pivots.  The
+// multipliers are kept so the adjoint solve (the matrix is symmetric) only touches right-hand
+// sides.  oracle/reduced_proto.py is the readable numpy statement of the same algebra and
+// tests/test_reduced_formulation.py checks it against the banded oracle.
+// ============================================================================
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "args.h"
+#include "hermite_constants.cuh"
+
+namespace mincob {
+
+
+template <int V>
+struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
+template <>
+struct Log2<1> { static constexpr int value = 0; };
+
+__host__ __device__ constexpr double cfact(int d) { return d <= 1 ? 1.0 : d * cfact(d - 1); }
+__host__ __device__ constexpr double cfall(int k, int d) { return d == 0 ? 1.0 : (k - d + 1) * cfall(k, d - 1); }  // k!/(k-d)!
+
+template <int LPT>
+__device__ __forceinline__ unsigned group_mask() {
+    if (LPT == 32) return 0xffffffffu;
+    return ((1u << (LPT & 31)) - 1u) << (((threadIdx.x & 31) / LPT) * LPT);
+}
+template <int LPT> __device__ __forceinline__ double sh_up(unsigned m, double v, int d) { return __shfl_up_sync(m, v, d, LPT); }
+template <int LPT> __device__ __forceinline__ double sh_dn(unsigned m, double v, int d) { return __shfl_down_sync(m, v, d, LPT); }
+template <int LPT> __device__ __forceinline__ double sh_xor(unsigned m, double v, int d) { return __shfl_xor_sync(m, v, d, LPT); }
+template <int LPT>
+__device__ __forceinline__ double group_sum(unsigned m, double v) {
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1) v += sh_xor<LPT>(m, v, o);
+    return v;  // butterfly: bitwise identical on every lane of the group
+}
+template <int LPT>
+__device__ __forceinline__ double group_max(unsigned m, double v) {
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1) v = fmax(v, sh_xor<LPT>(m, v, o));
+    return v;
+}
+
+// tau <-> T (upstream gcopter.hpp forwardT / backwardGradT)
+__device__ __forceinline__ double forward_t(double tau) {
+    return tau > 0.0 ? ((0.5 * tau + 1.0) * tau + 1.0) : 1.0 / ((0.5 * tau - 1.0) * tau + 1.0);
+}
+__device__ __forceinline__ double backward_grad_t(double tau, double gradT) {
+    if (tau > 0.0) return gradT * (tau + 1.0);
+    const double den = (0.5 * tau - 1.0) * tau + 1.0;
+    return gradT * (1.0 - tau) / (den * den);
+}
+// smoothedL1, gcopter/firi.hpp:60-84; caller guarantees x > 0.
+__device__ __forceinline__ void smoothed_l1_pos(double mu, double x, double &f, double &df) {
+    if (x > mu) { f = x - 0.5 * mu; df = 1.0; return; }
+    const double r = x / mu, r2 = r * r, h = mu - 0.5 * x;
+    f = h * r2 * r;
+    df = r2 * (-0.5 * r + 3.0 * h / mu);
+}
+
+// ---- small dense helpers (b = S-1 = 2 or 3) ---------------------------------------------
+template <int b>
+__device__ __forceinline__ void inv_small(const double (&d)[b][b], double (&o)[b][b]);
+template <>
+__device__ __forceinline__ void inv_small<2>(const double (&d)[2][2], double (&o)[2][2]) {
+    const double r = 1.0 / (d[0][0] * d[1][1] - d[0][1] * d[1][0]);
+    o[0][0] = d[1][1] * r; o[0][1] = -d[0][1] * r;
+    o[1][0] = -d[1][0] * r; o[1][1] = d[0][0] * r;
+}
+template <>
+__device__ __forceinline__ void inv_small<3>(const double (&d)[3][3], double (&o)[3][3]) {
+    const double c00 = d[1][1] * d[2][2] - d[1][2] * d[2][1];
+    const double c01 = d[1][2] * d[2][0] - d[1][0] * d[2][2];
+    const double c02 = d[1][0] * d[2][1] - d[1][1] * d[2][0];
+    const double r = 1.0 / (d[0][0] * c00 + d[0][1] * c01 + d[0][2] * c02);
+    o[0][0] = c00 * r; o[1][0] = c01 * r; o[2][0] = c02 * r;
+    o[0][1] = (d[0][2] * d[2][1] - d[0][1] * d[2][2]) * r;
+    o[1][1] = (d[0][0] * d[2][2] - d[0][2] * d[2][0]) * r;
+    o[2][1] = (d[0][1] * d[2][0] - d[0][0] * d[2][1]) * r;
+    o[0][2] = (d[0][1] * d[1][2] - d[0][2] * d[1][1]) * r;
+    o[1][2] = (d[0][2] * d[1][0] - d[0][0] * d[1][2]) * r;
+    o[2][2] = (d[0][0] * d[1][1] - d[0][1] * d[1][0]) * r;
+}
+
+// Per-lane (= per-piece) spline state kept between the forward solve and the adjoint.
+template <int S, int LPT>
+struct Spline {
+    static constexpr int D = 2 * S, b = S - 1, LEVELS = Log2<LPT>::value;
+    double T, iT, t5;       // duration, 1/T, T^(1-2S)
+    double sh[D][3];        // scaled boundary states L*s: rows 0..S-1 start, S..2S-1 end (row S holds dP = P1-P0)
+    double c[D][3];         // monomial coefficients, ascending powers (row k = c_k)
+    double al[LEVELS][b][b], ga[LEVELS][b][b], Dinv[b][b];  // PCR multipliers of this block row
+};
+
+// PCR forward pass on the right-hand side only (uses the stored multipliers).
+template <int S, int LPT>
+__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S, LPT> &sp, double (&r)[S - 1][3]) {
+    constexpr int b = S - 1;
+#pragma unroll
+    for (int l = 0; l < Spline<S, LPT>::LEVELS; ++l) {
+        const int s = 1 << l;
+        double rm[b][3], rp[b][3];
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                rm[a][x] = sh_up<LPT>(mask, r[a][x], s);
+                rp[a][x] = sh_dn<LPT>(mask, r[a][x], s);
+            }
+        const bool vm = lig >= s, vp = lig + s < LPT;
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = r[a][x];
+#pragma unroll
+                for (int k = 0; k < b; ++k) {
+                    if (vm) acc -= sp.al[l][a][k] * rm[k][x];
+                    if (vp) acc -= sp.ga[l][a][k] * rp[k][x];
+                }
+                r[a][x] = acc;
+            }
+    }
+    double y[b][3];
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < b; ++k) acc += sp.Dinv[a][k] * r[k][x];
+            y[a][x] = acc;
+        }
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) r[a][x] = y[a][x];
+}
+
+// setParameters: lane `lig` (< N active) holds piece lig with duration T, start position P0,
+// end position P1; hd/td are the head / tail derivatives 1..S-1 (used by lanes 0 / N-1).
+// Output: sp (coefficients + factorisation), chat (normalised coefficients c_k T^k).
+template <int S, int LPT>
+__device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, double Tin, const double (&P0)[3],
+                                             const double (&P1)[3], const double (&hd)[S - 1][3],
+                                             const double (&td)[S - 1][3], Spline<S, LPT> &sp,
+                                             double (&chat)[2 * S][3]) {
+    constexpr int D = 2 * S, b = S - 1;
+    using HK = HermiteK<S>;
+    const bool active = lig < N;
+    const double T = active ? Tin : 1.0;
+    const double iT = 1.0 / T;
+    double lam[S];
+    lam[0] = 1.0;
+#pragma unroll
+    for (int d = 1; d < S; ++d) lam[d] = lam[d - 1] * T;
+    double t5 = iT;
+#pragma unroll
+    for (int d = 1; d < 2 * S - 1; ++d) t5 *= iT;
+    sp.T = T; sp.iT = iT; sp.t5 = t5;
+    double dP[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) dP[x] = active ? P1[x] - P0[x] : 0.0;
+
+    // blocks of W(T) = t5 * lam_a lam_c What[a][c]; start unknown rows 1..S-1, end rows S+1..2S-1
+    double A[b][b], Bm[b][b], C[b][b], wa[b], wb[b];
+#pragma unroll
+    for (int a = 0; a < b; ++a) {
+        const double la = t5 * lam[a + 1];
+#pragma unroll
+        for (int c = 0; c < b; ++c) {
+            A[a][c] = la * lam[c + 1] * HK::W(1 + a, 1 + c);
+            Bm[a][c] = la * lam[c + 1] * HK::W(1 + a, S + 1 + c);
+            C[a][c] = la * lam[c + 1] * HK::W(S + 1 + a, S + 1 + c);
+        }
+        wa[a] = la * HK::W(1 + a, S);
+        wb[a] = la * HK::W(S + 1 + a, S);
+    }
+    // this piece's contribution to the right-hand side of its end junction (e) and start junction (f)
+    double e[b][3], f[b][3];
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double ev = wb[a] * dP[x], fv = wa[a] * dP[x];
+            if (lig == 0) {
+#pragma unroll
+                for (int c = 0; c < b; ++c) ev += Bm[c][a] * hd[c][x];
+            }
+            if (lig == N - 1) {
+#pragma unroll
+                for (int c = 0; c < b; ++c) fv += Bm[a][c] * td[c][x];
+            }
+            e[a][x] = ev; f[a][x] = fv;
+        }
+    // block row of junction `lig` (between piece lig-1 and piece lig)
+    double Dm[b][b], U[b][b], L[b][b], r[b][3];
+    const bool junction = (lig >= 1) && (lig < N);
+#pragma unroll
+    for (int a = 0; a < b; ++a) {
+#pragma unroll
+        for (int c = 0; c < b; ++c) {
+            const double Cp = sh_up<LPT>(mask, C[a][c], 1);
+            const double Bp = sh_up<LPT>(mask, Bm[c][a], 1);  // transposed: L = B_{j-1}^T
+            Dm[a][c] = junction ? Cp + A[a][c] : (a == c ? 1.0 : 0.0);
+            U[a][c] = (junction && lig < N - 1) ? Bm[a][c] : 0.0;
+            L[a][c] = (junction && lig >= 2) ? Bp : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double ep = sh_up<LPT>(mask, e[a][x], 1);
+            r[a][x] = junction ? -(ep + f[a][x]) : 0.0;
+        }
+    }
+    // parallel cyclic reduction
+#pragma unroll
+    for (int l = 0; l < Spline<S, LPT>::LEVELS; ++l) {
+        const int s = 1 << l;
+        double Di[b][b];
+        inv_small<b>(Dm, Di);
+        const bool vm = lig >= s, vp = lig + s < LPT;
+        double al[b][b], ga[b][b], Um[b][b], Lm[b][b], Up[b][b], Lp[b][b], rm[b][3], rp[b][3];
+        {
+            double Dim[b][b], Dip[b][b];
+#pragma unroll
+            for (int a = 0; a < b; ++a)
+#pragma unroll
+                for (int c = 0; c < b; ++c) {
+                    Dim[a][c] = sh_up<LPT>(mask, Di[a][c], s);
+                    Dip[a][c] = sh_dn<LPT>(mask, Di[a][c], s);
+                    Um[a][c] = sh_up<LPT>(mask, U[a][c], s);
+                    Lm[a][c] = sh_up<LPT>(mask, L[a][c], s);
+                    Up[a][c] = sh_dn<LPT>(mask, U[a][c], s);
+                    Lp[a][c] = sh_dn<LPT>(mask, L[a][c], s);
+                }
+#pragma unroll
+            for (int a = 0; a < b; ++a)
+#pragma unroll
+                for (int c = 0; c < b; ++c) {
+                    double sa = 0.0, sg = 0.0;
+#pragma unroll
+                    for (int k = 0; k < b; ++k) { sa += L[a][k] * Dim[k][c]; sg += U[a][k] * Dip[k][c]; }
+                    al[a][c] = vm ? sa : 0.0;
+                    ga[a][c] = vp ? sg : 0.0;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                rm[a][x] = sh_up<LPT>(mask, r[a][x], s);
+                rp[a][x] = sh_dn<LPT>(mask, r[a][x], s);
+            }
+        double Ln[b][b], Un[b][b];
+#pragma unroll
+        for (int a = 0; a < b; ++a) {
+#pragma unroll
+            for (int c = 0; c < b; ++c) {
+                double dd = Dm[a][c], ln = 0.0, un = 0.0;
+#pragma unroll
+                for (int k = 0; k < b; ++k) {
+                    if (vm) { dd -= al[a][k] * Um[k][c]; ln -= al[a][k] * Lm[k][c]; }
+                    if (vp) { dd -= ga[a][k] * Lp[k][c]; un -= ga[a][k] * Up[k][c]; }
+                }
+                Dm[a][c] = dd; Ln[a][c] = ln; Un[a][c] = un;
+                sp.al[l][a][c] = al[a][c];
+                sp.ga[l][a][c] = ga[a][c];
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = r[a][x];
+#pragma unroll
+                for (int k = 0; k < b; ++k) {
+                    if (vm) acc -= al[a][k] * rm[k][x];
+                    if (vp) acc -= ga[a][k] * rp[k][x];
+                }
+                r[a][x] = acc;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int c = 0; c < b; ++c) { L[a][c] = Ln[a][c]; U[a][c] = Un[a][c]; }
+    }
+    inv_small<b>(Dm, sp.Dinv);
+    double y[b][3];
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < b; ++k) acc += sp.Dinv[a][k] * r[k][x];
+            y[a][x] = acc;
+        }
+    // boundary states of this piece, scaled: sh[d] = T^d * (d-th derivative)
+#pragma unroll
+    for (int x = 0; x < 3; ++x) { sp.sh[0][x] = active ? P0[x] : 0.0; sp.sh[S][x] = dP[x]; }
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double yn = sh_dn<LPT>(mask, y[a][x], 1);
+            const double ys = (lig == 0) ? hd[a][x] : y[a][x];
+            const double ye = (lig == N - 1) ? td[a][x] : yn;
+            sp.sh[1 + a][x] = active ? lam[a + 1] * ys : 0.0;
+            sp.sh[S + 1 + a][x] = active ? lam[a + 1] * ye : 0.0;
+        }
+    // Hermite -> monomial.  Hhat[k][0] == -Hhat[k][S] for k >= S: positions enter only through dP.
+    double ip = 1.0;  // iT^k
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double v;
+            if (k < S) {
+                v = sp.sh[k][x] * (1.0 / cfact(k));
+            } else {
+                v = HK::H(k, S) * dP[x];
+#pragma unroll
+                for (int d = 1; d < S; ++d) v += HK::H(k, d) * sp.sh[d][x] + HK::H(k, S + d) * sp.sh[S + d][x];
+            }
+            chat[k][x] = v;
+            sp.c[k][x] = v * ip;
+        }
+        ip *= iT;
+    }
+}
+
+// getEnergy + getEnergyPartialGradByCoeffs + getEnergyPartialGradByTimes for this piece
+// (SURVEY.md Appendix A.3 in normalised form: E_i = T^(1-2S) chat^T Qhat chat).
+template <int S, int LPT>
+__device__ __forceinline__ void energy_partials(const Spline<S, LPT> &sp, const double (&chat)[2 * S][3], bool active,
+                                                double &energy, double (&G)[2 * S][3], double &gT) {
+    constexpr int D = 2 * S;
+    using HK = HermiteK<S>;
+    double e = 0.0, et = 0.0;
+    double tp[D];  // T^k
+    tp[0] = 1.0;
+#pragma unroll
+    for (int k = 1; k < D; ++k) tp[k] = tp[k - 1] * sp.T;
+#pragma unroll
+    for (int k = 0; k < S; ++k)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) G[k][x] = 0.0;
+#pragma unroll
+    for (int a = S; a < D; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double qc = 0.0, qt = 0.0;
+#pragma unroll
+            for (int c = S; c < D; ++c) {
+                qc += HK::Q(a, c) * chat[c][x];
+                qt += (HK::Q(a, c) * (a + c - 2 * S + 1)) * chat[c][x];
+            }
+            e += chat[a][x] * qc;
+            et += chat[a][x] * qt;
+            G[a][x] = active ? 2.0 * sp.t5 * tp[a] * qc : 0.0;
+        }
+    energy = active ? sp.t5 * e : 0.0;
+    gT = active ? sp.t5 * sp.iT * et : 0.0;
+}
+
+// 256-bit read-only load of one half-plane row (nx,ny,nz,d); rows are 32-byte aligned.
+struct __align__(32) Plane { double x, y, z, w; };
+__device__ __forceinline__ Plane load_plane(const double *p) {
+    Plane r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+// attachPenaltyFunctional for this piece.  planes: this piece's rows.
+// Samples are processed in register blocks of JB so that each half-plane row is loaded once
+// per block instead of once per sample (L1 bandwidth, not DFMA, would bound the naive loop).
+template <int S, int LPT>
+__device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT> &sp, const double *planes,
+                                              int K, double &cost, double (&G)[2 * S][3], double &gT) {
+    constexpr int D = 2 * S, JB = 6;
+    const int kap = P.kappa;
+    const double step = sp.T / kap;
+    const double ikap = 1.0 / kap;
+    for (int j0 = 0; j0 <= kap; j0 += JB) {
+        double pos[JB][3];
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+            const double s = (j0 + jj) * step;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double v = sp.c[D - 1][x];
+#pragma unroll
+                for (int k = D - 2; k >= 0; --k) v = fma(v, s, sp.c[k][x]);
+                pos[jj][x] = v;
+            }
+        }
+        unsigned hit = 0u;
+        for (int k = 0; k < K; ++k) {
+            const Plane h = load_plane(planes + 4 * k);
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) {
+                const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
+                hit |= (v > 0.0 ? 1u : 0u) << jj;
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+            const int j = j0 + jj;
+            if (j > kap) break;
+            const double s = j * step;
+            // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
+            double pw[D];
+            pw[0] = 1.0;
+#pragma unroll
+            for (int k = 1; k < D; ++k) pw[k] = pw[k - 1] * s;
+            double vel[3], acc[3], jer[3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double v = 0.0, a = 0.0, jr = 0.0;
+#pragma unroll
+                for (int k = 1; k < D; ++k) v = fma(cfall(k, 1) * pw[k - 1], sp.c[k][x], v);
+#pragma unroll
+                for (int k = 2; k < D; ++k) a = fma(cfall(k, 2) * pw[k - 2], sp.c[k][x], a);
+#pragma unroll
+                for (int k = 3; k < D; ++k) jr = fma(cfall(k, 3) * pw[k - 3], sp.c[k][x], jr);
+                vel[x] = v; acc[x] = a; jer[x] = jr;
+            }
+            const double vv = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - P.vmax2;
+            const double aa = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] - P.amax2;
+            const double jj2 = jer[0] * jer[0] + jer[1] * jer[1] + jer[2] * jer[2] - P.jmax2;
+            const bool hp = (hit >> jj) & 1u;
+            if (hp || vv > 0.0 || aa > 0.0 || jj2 > 0.0) {
+                double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
+                double fv, df;
+                if (hp) {
+                    for (int k = 0; k < K; ++k) {
+                        const Plane h = load_plane(planes + 4 * k);
+                        const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
+                        if (v > 0.0) {
+                            smoothed_l1_pos(P.mu, v, fv, df);
+                            const double wd = P.w_pos * df;
+                            gP[0] += wd * h.x; gP[1] += wd * h.y; gP[2] += wd * h.z;
+                            pena += P.w_pos * fv;
+                        }
+                    }
+                }
+                if (vv > 0.0) {
+                    smoothed_l1_pos(P.mu, vv, fv, df);
+                    const double wd = P.w_vel * df * 2.0;
+                    gV[0] = wd * vel[0]; gV[1] = wd * vel[1]; gV[2] = wd * vel[2];
+                    pena += P.w_vel * fv;
+                }
+                if (aa > 0.0) {
+                    smoothed_l1_pos(P.mu, aa, fv, df);
+                    const double wd = P.w_acc * df * 2.0;
+                    gA[0] = wd * acc[0]; gA[1] = wd * acc[1]; gA[2] = wd * acc[2];
+                    pena += P.w_acc * fv;
+                }
+                if (jj2 > 0.0) {
+                    smoothed_l1_pos(P.mu, jj2, fv, df);
+                    const double wd = P.w_jerk * df * 2.0;
+                    gJ[0] = wd * jer[0]; gJ[1] = wd * jer[1]; gJ[2] = wd * jer[2];
+                    pena += P.w_jerk * fv;
+                }
+                const double node = (j == 0 || j == kap) ? 0.5 : 1.0;
+                const double w = node * step;
+                double dsum = 0.0;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    double sn = 0.0;
+#pragma unroll
+                    for (int k = 4; k < D; ++k) sn = fma(cfall(k, 4) * pw[k - 4], sp.c[k][x], sn);
+                    dsum += gP[x] * vel[x] + gV[x] * acc[x] + gA[x] * jer[x] + gJ[x] * sn;
+                    const double wP = w * gP[x], wV = w * gV[x], wA = w * gA[x], wJ = w * gJ[x];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        double t = pw[k] * wP;
+                        if (k >= 1) t = fma(cfall(k, 1) * pw[k - 1], wV, t);
+                        if (k >= 2) t = fma(cfall(k, 2) * pw[k - 2], wA, t);
+                        if (k >= 3) t = fma(cfall(k, 3) * pw[k - 3], wJ, t);
+                        G[k][x] += t;
+                    }
+                }
+                gT += dsum * (j * ikap) * w + node * pena * ikap;
+                cost += w * pena;
+            }
+        }
+    }
+}
+
+// propogateGrad: G = dF/dc_i, gTp = partial dF/dT_i  ->  total dJ/dq_lig (junction lig, lanes
+// 1..N-1) and dJ/dT_lig (lanes 0..N-1).  See oracle/reduced_proto.py for the derivation.
+template <int S, int LPT>
+__device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, const Spline<S, LPT> &sp,
+                                               const double (&G)[2 * S][3], double gTp, double (&gq)[3], double &gT) {
+    constexpr int D = 2 * S, b = S - 1;
+    using HK = HermiteK<S>;
+    const bool active = lig < N;
+    const bool junction = (lig >= 1) && active;
+    // ghat_k = G_k / T^k ; z = Hhat^T ghat ; through-H time term  -(1/T) sum_k k G_k.c_k
+    double gh[D][3];
+    double ip = 1.0, kGc = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            gh[k][x] = G[k][x] * ip;
+            kGc += (double)k * G[k][x] * sp.c[k][x];
+        }
+        ip *= sp.iT;
+    }
+    double z[D][3];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double v = (d < S) ? gh[d][x] * (1.0 / cfact(d)) : 0.0;
+#pragma unroll
+            for (int k = S; k < D; ++k) v += HK::H(k, d) * gh[k][x];
+            z[d][x] = v;
+        }
+    double lam[S];
+    lam[0] = 1.0;
+#pragma unroll
+    for (int d = 1; d < S; ++d) lam[d] = lam[d - 1] * sp.T;
+    // gather at junctions: g_y[j] = (L z)_{end, piece j-1} + (L z)_{start, piece j}
+    double r[b][3], gp[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        const double pe = sh_up<LPT>(mask, active ? z[S][x] : 0.0, 1);
+        gp[x] = junction ? pe + z[0][x] : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double ee = sh_up<LPT>(mask, active ? lam[a + 1] * z[S + 1 + a][x] : 0.0, 1);
+            r[a][x] = junction ? ee + lam[a + 1] * z[1 + a][x] : 0.0;
+        }
+    pcr_apply<S, LPT>(mask, lig, sp, r);  // r <- mu_lig
+    // m_i = [0, mu_i ; 0, mu_{i+1}], scaled by L
+    double lm[D][3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) { lm[0][x] = 0.0; lm[S][x] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            const double mn = sh_dn<LPT>(mask, r[a][x], 1);
+            lm[1 + a][x] = junction ? lam[a + 1] * r[a][x] : 0.0;
+            lm[S + 1 + a][x] = (lig < N - 1) ? lam[a + 1] * mn : 0.0;
+        }
+    // wm = What (L m), ws = What (L s)  (positions through dP: What[:,0] == -What[:,S])
+    double acc_ms = 0.0, acc_dms = 0.0, acc_dsm = 0.0, zds = 0.0;
+    double wm0[3], wmS[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        double wm[D], ws[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            double vm = 0.0, vs = HK::W(a, S) * sp.sh[S][x];
+#pragma unroll
+            for (int d = 1; d < S; ++d) {
+                vm += HK::W(a, d) * lm[d][x] + HK::W(a, S + d) * lm[S + d][x];
+                vs += HK::W(a, d) * sp.sh[d][x] + HK::W(a, S + d) * sp.sh[S + d][x];
+            }
+            wm[a] = vm; ws[a] = vs;
+        }
+        wm0[x] = wm[0]; wmS[x] = wm[S];
+#pragma unroll
+        for (int d = 1; d < S; ++d) {
+            acc_ms += lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d];
+            acc_dms += (double)d * (lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d]);
+            acc_dsm += (double)d * (sp.sh[d][x] * wm[d] + sp.sh[S + d][x] * wm[S + d]);
+            zds += (double)d * (z[d][x] * sp.sh[d][x] + z[S + d][x] * sp.sh[S + d][x]);
+        }
+    }
+    // dJ/dq_j = g_p[j] - t5_j wm_j[0] - (t5 wm[S])_{j-1}
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        const double prev = sh_up<LPT>(mask, active ? sp.t5 * wmS[x] : 0.0, 1);
+        gq[x] = junction ? gp[x] - sp.t5 * wm0[x] - prev : 0.0;
+    }
+    // dJ/dT_i = partial - (1/T) sum k G_k.c_k + z.(L' s) - m^T W' s ;  L' = (d/T) L
+    const double mWs = sp.t5 * sp.iT * (-(double)(2 * S - 1) * acc_ms + acc_dms + acc_dsm);
+    gT = active ? gTp + sp.iT * (zds - kGc) - mWs : 0.0;
+}
+
+// ---- problem view ---------------------------------------------------------------------
+struct ProblemView {
+    const double *head;    // [S][3]
+    const double *tail;    // [S][3]
+    const double *planes;  // [N][K][4] or nullptr
+    const int *hrows;      // [N] or nullptr
+    int K;
+};
+
+// Whole cost functional for the group's trajectory.  xt = tau_lig, xq = q_lig (lanes 1..N-1).
+// Returns f on every lane of the group; gt = dJ/dtau_lig, gq = dJ/dq_lig.
+template <int S, int LPT>
+__device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N,
+                                                  const ProblemView &pv, double xt, const double (&xq)[3],
+                                                  double &gt, double (&gq)[3]) {
+    constexpr int D = 2 * S, b = S - 1;
+    const bool active = lig < N;
+    double P0[3], P1[3], hd[b][3], td[b][3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        const double qn = sh_dn<LPT>(mask, xq[x], 1);
+        P0[x] = (lig == 0) ? pv.head[x] : xq[x];
+        P1[x] = (lig == N - 1) ? pv.tail[x] : qn;
+    }
+#pragma unroll
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            hd[a][x] = (lig == 0) ? pv.head[(a + 1) * 3 + x] : 0.0;
+            td[a][x] = (lig == N - 1) ? pv.tail[(a + 1) * 3 + x] : 0.0;
+        }
+    const double T = active ? forward_t(xt) : 1.0;
+    Spline<S, LPT> sp;
+    double chat[D][3];
+    spline_solve<S, LPT>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
+    double cost, G[D][3], gTp;
+    energy_partials<S, LPT>(sp, chat, active, cost, G, gTp);
+    if (P.penalties && active) {
+        const int K = pv.hrows ? min(pv.hrows[lig], pv.K) : 0;
+        penalty_piece<S, LPT>(P, sp, pv.planes + (size_t)lig * pv.K * 4, pv.planes ? K : 0, cost, G, gTp);
+    }
+    double gT;
+    spline_adjoint<S, LPT>(mask, lig, N, sp, G, gTp, gq, gT);
+    if (active) cost += P.rho * T;
+    gt = active ? backward_grad_t(xt, gT + P.rho) : 0.0;
+    return group_sum<LPT>(mask, cost);
+}
+
+}  // namespace mincob

@@ -1,0 +1,571 @@
+// ============================================================================
+// mincob.cu -- C-ABI (include/mincob.h) over the sm_100a kernels.  Host side is plain C++:
+// argument checks, device buffers, launches, stream/event plumbing, NCCL via dlopen.
+// There is no CPU compute path in this file: without a CUDA device every compute entry point
+// fails with MINCOB_E_CUDA.
+// ============================================================================
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mincob.h"
+#include "launch.h"
+
+using namespace mincob;
+
+// ---- NCCL through dlopen (so the library loads, and its symbols can be listed, without NCCL) --
+typedef struct ncclComm *ncclComm_t;
+struct NcclUid { char b[128]; };
+typedef int (*nccl_get_uid_t)(NcclUid *);
+typedef int (*nccl_init_rank_t)(ncclComm_t *, int, NcclUid, int);
+typedef int (*nccl_allgather_t)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+typedef int (*nccl_destroy_t)(ncclComm_t);
+typedef const char *(*nccl_errstr_t)(int);
+
+static struct {
+    void *lib;
+    nccl_get_uid_t get_uid;
+    nccl_init_rank_t init_rank;
+    nccl_allgather_t allgather;
+    nccl_destroy_t destroy;
+    nccl_errstr_t errstr;
+} g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static bool nccl_load() {
+    if (g_nccl.lib) return true;
+    // RTLD_DEFAULT first: inside a torch process libnccl is already mapped.
+    void *probe = dlsym(RTLD_DEFAULT, "ncclGetUniqueId");
+    void *lib = nullptr;
+    if (!probe) {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+    }
+    void *h = lib ? lib : RTLD_DEFAULT;
+    g_nccl.get_uid = (nccl_get_uid_t)dlsym(h, "ncclGetUniqueId");
+    g_nccl.init_rank = (nccl_init_rank_t)dlsym(h, "ncclCommInitRank");
+    g_nccl.allgather = (nccl_allgather_t)dlsym(h, "ncclAllGather");
+    g_nccl.destroy = (nccl_destroy_t)dlsym(h, "ncclCommDestroy");
+    g_nccl.errstr = (nccl_errstr_t)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allgather || !g_nccl.destroy) return false;
+    g_nccl.lib = lib ? lib : (void *)1;
+    return true;
+}
+
+// ---- handle -------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct mincob_ctx {
+    mincob_params prm;
+    DevParams dp;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool timed = false;
+    int sm_count = 0;
+    // problems (device pointers; owned only when they point into the DevBufs below)
+    int B = 0, N = 0, K = 0;
+    const double *head = nullptr, *tail = nullptr, *hpolys = nullptr;
+    const int *hrows = nullptr;
+    DevBuf b_head, b_tail, b_hpolys, b_hrows;          // set_problems (host) staging
+    DevBuf b_x, b_f, b_g, b_status, b_iters, b_evals, b_coeffs, b_T;  // host-pointer entry points
+    DevBuf b_m0, b_m1, b_m2, b_m3, b_m4, b_m5, b_m6, b_m7, b_m8;      // minco_forward / propagate
+    int *counter = nullptr;
+    unsigned long long *total_evals = nullptr;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    std::string err;
+};
+
+static int fail(mincob_ctx *h, int code, const char *fmt, ...) {
+    if (h) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+#define CU(h, call)                                                                                \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(h, MINCOB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static int ensure(mincob_ctx *h, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(h, MINCOB_E_ALLOC, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    b.cap = bytes;
+    return 0;
+}
+static void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+static int derive(mincob_ctx *h) {
+    const mincob_params &p = h->prm;
+    if (p.S != 3 && p.S != 4) return fail(h, MINCOB_E_INVALID, "S must be 3 or 4 (got %d)", p.S);
+    if (p.kappa < 1) return fail(h, MINCOB_E_INVALID, "kappa must be >= 1");
+    if (!(p.mu > 0.0)) return fail(h, MINCOB_E_INVALID, "mu must be > 0");
+    DevParams &d = h->dp;
+    d.kappa = p.kappa; d.mu = p.mu;
+    d.w_pos = p.w_pos; d.w_vel = p.w_vel; d.w_acc = p.w_acc; d.w_jerk = p.w_jerk;
+    d.vmax2 = p.v_max * p.v_max; d.amax2 = p.a_max * p.a_max; d.jmax2 = p.j_max * p.j_max;
+    d.rho = p.rho;
+    d.penalties = (p.w_pos != 0.0 || p.w_vel != 0.0 || p.w_acc != 0.0 || p.w_jerk != 0.0) ? 1 : 0;
+    d.mem = p.mem_size; d.past = p.past; d.max_iter = p.max_iterations; d.max_ls = p.max_linesearch;
+    d.g_eps = p.g_epsilon; d.delta = p.delta; d.min_step = p.min_step; d.max_step = p.max_step;
+    d.f_dec = p.f_dec_coeff; d.s_curv = p.s_curv_coeff; d.cautious = p.cautious_factor; d.mach_prec = p.machine_prec;
+    return 0;
+}
+
+// lbfgs.hpp:450-495 parameter validation; returns 0 or the LBFGSERR_* the reference would return.
+static int lbfgs_param_code(const mincob_params &p, int n) {
+    if (n <= 0) return LBFGSERR_INVALID_N;
+    if (p.mem_size <= 0) return LBFGSERR_INVALID_MEMSIZE;
+    if (p.g_epsilon < 0.0) return LBFGSERR_INVALID_GEPSILON;
+    if (p.past < 0) return LBFGSERR_INVALID_TESTPERIOD;
+    if (p.delta < 0.0) return LBFGSERR_INVALID_DELTA;
+    if (p.min_step < 0.0) return LBFGSERR_INVALID_MINSTEP;
+    if (p.max_step < p.min_step) return LBFGSERR_INVALID_MAXSTEP;
+    if (!(p.f_dec_coeff > 0.0 && p.f_dec_coeff < 1.0)) return LBFGSERR_INVALID_FDECCOEFF;
+    if (!(p.s_curv_coeff < 1.0 && p.s_curv_coeff > p.f_dec_coeff)) return LBFGSERR_INVALID_SCURVCOEFF;
+    if (!(p.machine_prec > 0.0)) return LBFGSERR_INVALID_MACHINEPREC;
+    if (p.max_linesearch <= 0) return LBFGSERR_INVALID_MAXLINESEARCH;
+    return 0;
+}
+
+// kernels are instantiated per (S, LPT) in kernels_inst.cu (one object each, built in parallel)
+static int lpt_index(int N) { return N <= 8 ? 0 : (N <= 16 ? 1 : 2); }
+static const LaunchTable *table_for(int S, int N) {
+    static const LaunchTable *tabs[2][3] = {
+        {mincob_table_3_8(), mincob_table_3_16(), mincob_table_3_32()},
+        {mincob_table_4_8(), mincob_table_4_16(), mincob_table_4_32()}};
+    return tabs[S == 3 ? 0 : 1][lpt_index(N)];
+}
+static int launched(mincob_ctx *h, const LaunchResult &r, const char *what) {
+    if (r.err != cudaSuccess) return fail(h, MINCOB_E_CUDA, "%s: %s", what, cudaGetErrorString(r.err));
+    if (r.code) return fail(h, r.code, "%s: kernel does not fit (dynamic smem %zu B); lower mem_size", what, r.smem);
+    return 0;
+}
+static int do_evaluate(mincob_ctx *h, const BatchArgs &a) {
+    return launched(h, table_for(h->prm.S, a.N)->evaluate(h->stream, h->sm_count, h->dp, a), "evaluate_kernel");
+}
+static int do_optimize(mincob_ctx *h, const BatchArgs &a) {
+    return launched(h, table_for(h->prm.S, a.N)->optimize(h->stream, h->sm_count, h->dp, a), "optimize_kernel");
+}
+static int do_minco(mincob_ctx *h, const MincoArgs &a, int propagate) {
+    return launched(h, table_for(h->prm.S, a.N)->minco(h->stream, h->sm_count, a, propagate), "minco_kernel");
+}
+
+static int have_problems(mincob_ctx *h) {
+    if (!h) return MINCOB_E_INVALID;
+    if (h->B <= 0 || !h->head || !h->tail) return fail(h, MINCOB_E_STATE, "set_problems has not been called");
+    return 0;
+}
+static BatchArgs base_args(mincob_ctx *h) {
+    BatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = h->B; a.N = h->N; a.K = h->K;
+    a.head = h->head; a.tail = h->tail; a.hpolys = h->hpolys; a.hrows = h->hrows;
+    a.counter = h->counter; a.total_evals = h->total_evals;
+    return a;
+}
+
+extern "C" {
+
+int mincob_version(void) { return 100; }
+
+int mincob_default_params(mincob_params *p, int S) {
+    if (!p || (S != 3 && S != 4)) return MINCOB_E_INVALID;
+    memset(p, 0, sizeof *p);
+    p->S = S; p->kappa = 16; p->mu = 1.0e-2;
+    p->w_pos = p->w_vel = p->w_acc = p->w_jerk = 1.0e4;
+    p->v_max = 4.0; p->a_max = 6.0; p->j_max = 12.0; p->rho = 20.0;
+    p->mem_size = 8; p->past = 3; p->max_iterations = 1000; p->max_linesearch = 64;
+    p->g_epsilon = 0.0; p->delta = 1.0e-5; p->min_step = 1.0e-32; p->max_step = 1.0e20;
+    p->f_dec_coeff = 1.0e-4; p->s_curv_coeff = 0.9; p->cautious_factor = 1.0e-6; p->machine_prec = 1.0e-16;
+    return 0;
+}
+
+const char *mincob_strerror(int code) {
+    switch (code) {
+        case MINCOB_OK: return "ok";
+        case MINCOB_E_INVALID: return "invalid argument";
+        case MINCOB_E_CUDA: return "CUDA error or no CUDA device (this library has no CPU path)";
+        case MINCOB_E_STATE: return "call order error";
+        case MINCOB_E_NCCL: return "NCCL unavailable or failed";
+        case MINCOB_E_ALLOC: return "device allocation failed";
+        default: return "unknown mincob error";
+    }
+}
+
+// Messages follow lbfgs_strerror, gcopter/lbfgs.hpp:724-800 (same meaning per code).
+const char *mincob_lbfgs_strerror(int s) {
+    switch (s) {
+        case LBFGS_CONVERGENCE: return "Success: reached convergence (g_epsilon).";
+        case LBFGS_STOP: return "Success: met stopping criteria (past f decrease less than delta).";
+        case LBFGS_CANCELED: return "The iteration has been canceled by the monitor callback.";
+        case LBFGSERR_UNKNOWNERROR: return "Unknown error.";
+        case LBFGSERR_INVALID_N: return "Invalid number of variables specified.";
+        case LBFGSERR_INVALID_MEMSIZE: return "Invalid parameter lbfgs_parameter_t::mem_size specified.";
+        case LBFGSERR_INVALID_GEPSILON: return "Invalid parameter lbfgs_parameter_t::g_epsilon specified.";
+        case LBFGSERR_INVALID_TESTPERIOD: return "Invalid parameter lbfgs_parameter_t::past specified.";
+        case LBFGSERR_INVALID_DELTA: return "Invalid parameter lbfgs_parameter_t::delta specified.";
+        case LBFGSERR_INVALID_MINSTEP: return "Invalid parameter lbfgs_parameter_t::min_step specified.";
+        case LBFGSERR_INVALID_MAXSTEP: return "Invalid parameter lbfgs_parameter_t::max_step specified.";
+        case LBFGSERR_INVALID_FDECCOEFF: return "Invalid parameter lbfgs_parameter_t::f_dec_coeff specified.";
+        case LBFGSERR_INVALID_SCURVCOEFF: return "Invalid parameter lbfgs_parameter_t::s_curv_coeff specified.";
+        case LBFGSERR_INVALID_MACHINEPREC: return "Invalid parameter lbfgs_parameter_t::machine_prec specified.";
+        case LBFGSERR_INVALID_MAXLINESEARCH: return "Invalid parameter lbfgs_parameter_t::max_linesearch specified.";
+        case LBFGSERR_INVALID_FUNCVAL: return "The function value became NaN or Inf.";
+        case LBFGSERR_MINIMUMSTEP: return "The line-search step became smaller than lbfgs_parameter_t::min_step.";
+        case LBFGSERR_MAXIMUMSTEP: return "The line-search step became larger than lbfgs_parameter_t::max_step.";
+        case LBFGSERR_MAXIMUMLINESEARCH: return "Line search reaches the maximum try number, assumptions not satisfied or precision not achievable.";
+        case LBFGSERR_MAXIMUMITERATION: return "The algorithm routine reaches the maximum number of iterations.";
+        case LBFGSERR_WIDTHTOOSMALL: return "Relative search interval width is at least lbfgs_parameter_t::machine_prec.";
+        case LBFGSERR_INVALIDPARAMETERS: return "A logic error (negative line-search step) occurred.";
+        case LBFGSERR_INCREASEGRADIENT: return "The current search direction increases the cost function value.";
+        default: return "(unknown)";
+    }
+}
+
+const char *mincob_last_error(mincob_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int mincob_create(mincob_handle *out, const mincob_params *params, int device) {
+    if (!out || !params) return MINCOB_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MINCOB_E_CUDA;
+    mincob_ctx *h = new (std::nothrow) mincob_ctx;
+    if (!h) return MINCOB_E_ALLOC;
+    h->prm = *params;
+    h->device = device;
+    int rc = derive(h);
+    if (rc) { delete h; return rc; }
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return MINCOB_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MINCOB_E_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MINCOB_E_CUDA; }
+    h->stream = h->own_stream;
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    if (cudaMalloc((void **)&h->counter, sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&h->total_evals, sizeof(unsigned long long)) != cudaSuccess) {
+        mincob_destroy(h);
+        return MINCOB_E_ALLOC;
+    }
+    *out = h;
+    return 0;
+}
+
+int mincob_destroy(mincob_handle h) {
+    if (!h) return MINCOB_E_INVALID;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+    DevBuf *bufs[] = {&h->b_head, &h->b_tail, &h->b_hpolys, &h->b_hrows, &h->b_x, &h->b_f, &h->b_g, &h->b_status,
+                      &h->b_iters, &h->b_evals, &h->b_coeffs, &h->b_T, &h->b_m0, &h->b_m1, &h->b_m2, &h->b_m3,
+                      &h->b_m4, &h->b_m5, &h->b_m6, &h->b_m7, &h->b_m8};
+    for (DevBuf *b : bufs) release(*b);
+    if (h->counter) cudaFree(h->counter);
+    if (h->total_evals) cudaFree(h->total_evals);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int mincob_set_params(mincob_handle h, const mincob_params *p) {
+    if (!h || !p) return MINCOB_E_INVALID;
+    const mincob_params old = h->prm;
+    h->prm = *p;
+    int rc = derive(h);
+    if (rc) { h->prm = old; derive(h); }
+    return rc;
+}
+
+int mincob_set_stream(mincob_handle h, void *s) {
+    if (!h) return MINCOB_E_INVALID;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return 0;
+}
+
+int mincob_synchronize(mincob_handle h) {
+    if (!h) return MINCOB_E_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mincob_last_kernel_ms(mincob_handle h, float *ms, int *launches) {
+    if (!h) return MINCOB_E_INVALID;
+    if (!h->timed) return fail(h, MINCOB_E_STATE, "no evaluate/optimize call has been timed yet");
+    CU(h, cudaEventSynchronize(h->ev1));
+    float t = 0.f;
+    CU(h, cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    if (ms) *ms = t;
+    if (launches) *launches = h->last_launches;
+    return 0;
+}
+
+static int check_shape(mincob_ctx *h, int B, int N, int K) {
+    if (B <= 0) return fail(h, MINCOB_E_INVALID, "B must be > 0");
+    if (N < 1 || N > MINCOB_MAX_PIECES) return fail(h, MINCOB_E_INVALID, "N must be in [1,%d] (got %d)", MINCOB_MAX_PIECES, N);
+    if (K < 0) return fail(h, MINCOB_E_INVALID, "K must be >= 0");
+    return 0;
+}
+
+int mincob_set_problems_device(mincob_handle h, int B, int N, int K, const double *head, const double *tail,
+                               const double *hpolys, const int32_t *hrows) {
+    if (!h || !head || !tail) return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, K);
+    if (rc) return rc;
+    if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
+    if (hpolys && ((uintptr_t)hpolys & 31u)) return fail(h, MINCOB_E_INVALID, "hpolys must be 32-byte aligned");
+    h->B = B; h->N = N; h->K = K;
+    h->head = head; h->tail = tail;
+    h->hpolys = K > 0 ? hpolys : nullptr;
+    h->hrows = K > 0 ? (const int *)hrows : nullptr;
+    return 0;
+}
+
+int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head, const double *tail,
+                        const double *hpolys, const int32_t *hrows) {
+    if (!h || !head || !tail) return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, K);
+    if (rc) return rc;
+    if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
+    CU(h, cudaSetDevice(h->device));
+    const int S = h->prm.S;
+    const size_t nb = (size_t)B * S * 3 * sizeof(double), np = (size_t)B * N * K * 4 * sizeof(double),
+                 nr = (size_t)B * N * sizeof(int);
+    if ((rc = ensure(h, h->b_head, nb)) || (rc = ensure(h, h->b_tail, nb))) return rc;
+    CU(h, cudaMemcpyAsync(h->b_head.p, head, nb, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->b_tail.p, tail, nb, cudaMemcpyHostToDevice, h->stream));
+    if (K > 0) {
+        if ((rc = ensure(h, h->b_hpolys, np)) || (rc = ensure(h, h->b_hrows, nr))) return rc;
+        CU(h, cudaMemcpyAsync(h->b_hpolys.p, hpolys, np, cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->b_hrows.p, hrows, nr, cudaMemcpyHostToDevice, h->stream));
+    }
+    return mincob_set_problems_device(h, B, N, K, (const double *)h->b_head.p, (const double *)h->b_tail.p,
+                                      K > 0 ? (const double *)h->b_hpolys.p : nullptr,
+                                      K > 0 ? (const int32_t *)h->b_hrows.p : nullptr);
+}
+
+int mincob_evaluate_device(mincob_handle h, const double *x, double *f, double *g) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!x || !f || !g) return fail(h, MINCOB_E_INVALID, "x, f, g must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    BatchArgs a = base_args(h);
+    a.x_in = x; a.f_out = f; a.g_out = g;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    rc = do_evaluate(h, a);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = true; h->last_launches = 1;
+    return 0;
+}
+
+int mincob_evaluate(mincob_handle h, const double *x, double *f, double *g) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!x || !f || !g) return fail(h, MINCOB_E_INVALID, "x, f, g must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)h->N + 3 * (h->N - 1), nx = (size_t)h->B * n * sizeof(double), nf = (size_t)h->B * sizeof(double);
+    if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_g, nx)) || (rc = ensure(h, h->b_f, nf))) return rc;
+    CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
+    rc = mincob_evaluate_device(h, (const double *)h->b_x.p, (double *)h->b_f.p, (double *)h->b_g.p);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(f, h->b_f.p, nf, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(g, h->b_g.p, nx, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static __global__ void fill_status_kernel(int *status, int B, int code) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) status[i] = code;
+}
+
+int mincob_optimize_device(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
+                           double *coeffs, double *T) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const int n = h->N + 3 * (h->N - 1);
+    const int pc = lbfgs_param_code(h->prm, n);
+    if (pc) {  // lbfgs.hpp:450-495: the reference returns the code before touching x
+        if (status) {
+            fill_status_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(status, h->B, pc);
+            CU(h, cudaGetLastError());
+        }
+        h->timed = false;
+        return 0;
+    }
+    if (h->prm.mem_size > MINCOB_MAX_MEM) return fail(h, MINCOB_E_INVALID, "mem_size > %d not supported", MINCOB_MAX_MEM);
+    if (h->prm.past > MINCOB_MAX_PAST) return fail(h, MINCOB_E_INVALID, "past > %d not supported", MINCOB_MAX_PAST);
+    BatchArgs a = base_args(h);
+    a.x = x; a.f_out = f; a.status = status; a.iters = iters; a.evals = evals; a.coeffs = coeffs; a.T = T;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    rc = do_optimize(h, a);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = true; h->last_launches = 1;
+    return 0;
+}
+
+int mincob_optimize(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
+                    double *coeffs, double *T) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const size_t B = h->B, N = h->N, n = N + 3 * (N - 1), S = h->prm.S;
+    const size_t nx = B * n * 8, nf = B * 8, ni = B * 4, nc = B * N * 3 * 2 * S * 8, nt = B * N * 8;
+    if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_f, nf)) || (rc = ensure(h, h->b_status, ni)) ||
+        (rc = ensure(h, h->b_iters, ni)) || (rc = ensure(h, h->b_evals, ni)) || (rc = ensure(h, h->b_coeffs, nc)) ||
+        (rc = ensure(h, h->b_T, nt)))
+        return rc;
+    CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
+    rc = mincob_optimize_device(h, (double *)h->b_x.p, (double *)h->b_f.p, (int32_t *)h->b_status.p,
+                                (int32_t *)h->b_iters.p, (int32_t *)h->b_evals.p, coeffs ? (double *)h->b_coeffs.p : nullptr,
+                                T ? (double *)h->b_T.p : nullptr);
+    if (rc) return rc;
+    const bool ran = h->timed;  // false when the parameter check short-circuited
+    if (ran) CU(h, cudaMemcpyAsync(x, h->b_x.p, nx, cudaMemcpyDeviceToHost, h->stream));
+    if (f && ran) CU(h, cudaMemcpyAsync(f, h->b_f.p, nf, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(status, h->b_status.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    if (iters && ran) CU(h, cudaMemcpyAsync(iters, h->b_iters.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    if (evals && ran) CU(h, cudaMemcpyAsync(evals, h->b_evals.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    if (coeffs && ran) CU(h, cudaMemcpyAsync(coeffs, h->b_coeffs.p, nc, cudaMemcpyDeviceToHost, h->stream));
+    if (T && ran) CU(h, cudaMemcpyAsync(T, h->b_T.p, nt, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- MINCO building blocks (host pointers) -------------------------------------------------
+static int up(mincob_ctx *h, DevBuf &b, const void *src, size_t bytes) {
+    int rc = ensure(h, b, bytes);
+    if (rc) return rc;
+    if (src && bytes) CU(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+static int down(mincob_ctx *h, void *dst, const DevBuf &b, size_t bytes) {
+    if (dst && bytes) CU(h, cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+int mincob_minco_forward(mincob_handle h, int B, int N, const double *head, const double *tail, const double *inPs,
+                         const double *ts, double *coeffs_asc, double *energy, double *gdC, double *gdT, double *flat) {
+    if (!h || !head || !tail || !ts || (N > 1 && !inPs)) return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, 0);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    const size_t S = h->prm.S, D = 2 * S;
+    const size_t nb = (size_t)B * S * 3 * 8, nq = (size_t)B * (N - 1) * 3 * 8, nt = (size_t)B * N * 8,
+                 nc = (size_t)B * D * N * 3 * 8, ne = (size_t)B * 8;
+    if ((rc = up(h, h->b_m0, head, nb)) || (rc = up(h, h->b_m1, tail, nb)) || (rc = up(h, h->b_m2, inPs, nq)) ||
+        (rc = up(h, h->b_m3, ts, nt)) || (rc = ensure(h, h->b_m4, nc)) || (rc = ensure(h, h->b_m5, ne)) ||
+        (rc = ensure(h, h->b_m6, nc)) || (rc = ensure(h, h->b_m7, nt)) || (rc = ensure(h, h->b_m8, nc)))
+        return rc;
+    MincoArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.N = N;
+    a.head = (double *)h->b_m0.p; a.tail = (double *)h->b_m1.p; a.inPs = (double *)h->b_m2.p; a.ts = (double *)h->b_m3.p;
+    a.coeffs_asc = (double *)h->b_m4.p; a.energy = (double *)h->b_m5.p; a.gdC = (double *)h->b_m6.p;
+    a.gdT = (double *)h->b_m7.p; a.flat = (double *)h->b_m8.p;
+    if ((rc = do_minco(h, a, 0))) return rc;
+    if ((rc = down(h, coeffs_asc, h->b_m4, nc)) || (rc = down(h, energy, h->b_m5, ne)) || (rc = down(h, gdC, h->b_m6, nc)) ||
+        (rc = down(h, gdT, h->b_m7, nt)) || (rc = down(h, flat, h->b_m8, nc)))
+        return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mincob_minco_propagate(mincob_handle h, int B, int N, const double *head, const double *tail, const double *inPs,
+                           const double *ts, const double *gdC, const double *gdT, double *gradByPoints,
+                           double *gradByTimes) {
+    if (!h || !head || !tail || !ts || !gdC || !gdT || !gradByTimes || (N > 1 && (!inPs || !gradByPoints)))
+        return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, 0);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    const size_t S = h->prm.S, D = 2 * S;
+    const size_t nb = (size_t)B * S * 3 * 8, nq = (size_t)B * (N - 1) * 3 * 8, nt = (size_t)B * N * 8,
+                 nc = (size_t)B * D * N * 3 * 8;
+    if ((rc = up(h, h->b_m0, head, nb)) || (rc = up(h, h->b_m1, tail, nb)) || (rc = up(h, h->b_m2, inPs, nq)) ||
+        (rc = up(h, h->b_m3, ts, nt)) || (rc = up(h, h->b_m4, gdC, nc)) || (rc = up(h, h->b_m5, gdT, nt)) ||
+        (rc = ensure(h, h->b_m6, nq)) || (rc = ensure(h, h->b_m7, nt)))
+        return rc;
+    MincoArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.N = N;
+    a.head = (double *)h->b_m0.p; a.tail = (double *)h->b_m1.p; a.inPs = (double *)h->b_m2.p; a.ts = (double *)h->b_m3.p;
+    a.gdC_in = (double *)h->b_m4.p; a.gdT_in = (double *)h->b_m5.p;
+    a.gradByPoints = (double *)h->b_m6.p; a.gradByTimes = (double *)h->b_m7.p;
+    if ((rc = do_minco(h, a, 1))) return rc;
+    if ((rc = down(h, gradByPoints, h->b_m6, nq)) || (rc = down(h, gradByTimes, h->b_m7, nt))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+int mincob_nccl_unique_id(void *uid) {
+    if (!uid) return MINCOB_E_INVALID;
+    if (!nccl_load()) return MINCOB_E_NCCL;
+    return g_nccl.get_uid((NcclUid *)uid) == 0 ? 0 : MINCOB_E_NCCL;
+}
+
+int mincob_comm_init(mincob_handle h, int nranks, int rank, const void *uid) {
+    if (!h || !uid || nranks < 1 || rank < 0 || rank >= nranks) return MINCOB_E_INVALID;
+    if (!nccl_load()) return fail(h, MINCOB_E_NCCL, "libnccl not found");
+    CU(h, cudaSetDevice(h->device));
+    NcclUid id;
+    memcpy(&id, uid, sizeof id);
+    const int rc = g_nccl.init_rank(&h->comm, nranks, id, rank);
+    if (rc != 0) return fail(h, MINCOB_E_NCCL, "ncclCommInitRank: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    h->nranks = nranks; h->rank = rank;
+    return 0;
+}
+
+int mincob_allgather_device(mincob_handle h, const double *send, double *recv, int64_t count) {
+    if (!h || !send || !recv || count < 0) return MINCOB_E_INVALID;
+    if (!h->comm) return fail(h, MINCOB_E_STATE, "mincob_comm_init has not been called");
+    CU(h, cudaSetDevice(h->device));
+    const int rc = g_nccl.allgather(send, recv, (size_t)count, /*ncclDouble*/ 8, h->comm, h->stream);
+    if (rc != 0) return fail(h, MINCOB_E_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return 0;
+}
+
+int mincob_comm_destroy(mincob_handle h) {
+    if (!h) return MINCOB_E_INVALID;
+    if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
+    h->comm = nullptr;
+    return 0;
+}
+
+}  // extern "C"
