@@ -30,7 +30,7 @@ SYMBOLS = [
     "mincob_set_problems", "mincob_set_problems_device", "mincob_evaluate", "mincob_evaluate_device",
     "mincob_optimize", "mincob_optimize_device", "mincob_last_kernel_ms", "mincob_minco_forward",
     "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
-    "mincob_comm_destroy",
+    "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
 ]
 
 
@@ -72,6 +72,9 @@ def load_library() -> C.CDLL:
     L.mincob_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
     L.mincob_allgather_device.argtypes = [_vp, _vp, _vp, C.c_int64]
     L.mincob_comm_destroy.argtypes = [_vp]
+    L.mincob_optimize_sharded.argtypes = [_vp] + [_vp] * 7
+    L.mincob_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
+    L.mincob_host_free.argtypes = [_vp]
     _lib = L
     return L
 
@@ -233,6 +236,28 @@ class MincoBatch:
 
     def allgather_device(self, send, recv, count_per_rank: int):
         self._check(self.L.mincob_allgather_device(self.h, _dev_ptr(send), _dev_ptr(recv), int(count_per_rank)))
+
+
+    def optimize_sharded_host_buffers(self, x, f, status, iters, evals, coeffs_all, T):
+        """Config 5 on caller-owned host arrays: optimize this rank's shard, all-gather the coefficients."""
+        self._check(self.L.mincob_optimize_sharded(self.h, _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(iters),
+                                                   _np_ptr(evals), _np_ptr(coeffs_all), _np_ptr(T)))
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array over page-locked host memory from mincob_host_alloc (freed when the array dies)."""
+    import weakref
+    L = load_library()
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = _vp()
+    rc = L.mincob_host_alloc(C.byref(p), max(nbytes, 8))
+    if rc != 0:
+        raise MincobError(f"mincob_host_alloc({nbytes}): {L.mincob_strerror(rc).decode()}")
+    buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, L.mincob_host_free, _vp(p.value))
+    return arr
 
 
 def lbfgs_strerror(status: int) -> str:

@@ -38,8 +38,18 @@ struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
 template <>
 struct Log2<1> { static constexpr int value = 0; };
 
-__host__ __device__ constexpr double cfact(int d) { return d <= 1 ? 1.0 : d * cfact(d - 1); }
-__host__ __device__ constexpr double cfall(int k, int d) { return d == 0 ? 1.0 : (k - d + 1) * cfall(k, d - 1); }  // k!/(k-d)!
+// d! and k!/(k-d)!: loop form (no recursion) so that they fold to literals once the surrounding
+// loops are unrolled, and stay cheap straight-line code if they are not.
+__host__ __device__ __forceinline__ constexpr double cfact(int d) {
+    double f = 1.0;
+    for (int u = 2; u <= d; ++u) f *= u;
+    return f;
+}
+__host__ __device__ __forceinline__ constexpr double cfall(int k, int d) {
+    double f = 1.0;
+    for (int u = 0; u < d; ++u) f *= (k - u);
+    return f;
+}
 
 template <int LPT>
 __device__ __forceinline__ unsigned group_mask() {
@@ -425,7 +435,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
             const int j = j0 + jj;
-            if (j > kap) break;
+            if (j <= kap) {
             const double s = j * step;
             // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
             double pw[D];
@@ -502,6 +512,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 }
                 gT += dsum * (j * ikap) * w + node * pena * ikap;
                 cost += w * pena;
+            }
             }
         }
     }

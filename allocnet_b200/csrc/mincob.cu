@@ -81,7 +81,7 @@ struct mincob_ctx {
     const double *head = nullptr, *tail = nullptr, *hpolys = nullptr;
     const int *hrows = nullptr;
     DevBuf b_head, b_tail, b_hpolys, b_hrows;          // set_problems (host) staging
-    DevBuf b_x, b_f, b_g, b_status, b_iters, b_evals, b_coeffs, b_T;  // host-pointer entry points
+    DevBuf b_x, b_f, b_g, b_status, b_iters, b_evals, b_coeffs, b_T, b_gather;  // host-pointer entry points
     DevBuf b_m0, b_m1, b_m2, b_m3, b_m4, b_m5, b_m6, b_m7, b_m8;      // minco_forward / propagate
     int *counter = nullptr;
     unsigned long long *total_evals = nullptr;
@@ -285,7 +285,7 @@ int mincob_destroy(mincob_handle h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
     DevBuf *bufs[] = {&h->b_head, &h->b_tail, &h->b_hpolys, &h->b_hrows, &h->b_x, &h->b_f, &h->b_g, &h->b_status,
-                      &h->b_iters, &h->b_evals, &h->b_coeffs, &h->b_T, &h->b_m0, &h->b_m1, &h->b_m2, &h->b_m3,
+                      &h->b_iters, &h->b_evals, &h->b_coeffs, &h->b_T, &h->b_gather, &h->b_m0, &h->b_m1, &h->b_m2, &h->b_m3,
                       &h->b_m4, &h->b_m5, &h->b_m6, &h->b_m7, &h->b_m8};
     for (DevBuf *b : bufs) release(*b);
     if (h->counter) cudaFree(h->counter);
@@ -559,6 +559,50 @@ int mincob_allgather_device(mincob_handle h, const double *send, double *recv, i
     const int rc = g_nccl.allgather(send, recv, (size_t)count, /*ncclDouble*/ 8, h->comm, h->stream);
     if (rc != 0) return fail(h, MINCOB_E_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     return 0;
+}
+
+int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
+                            double *coeffs_all, double *T) {
+    if (!h) return MINCOB_E_INVALID;
+    if (!h->comm || h->nranks == 1) return mincob_optimize(h, x, f, status, iters, evals, coeffs_all, T);
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!x || !coeffs_all) return fail(h, MINCOB_E_INVALID, "x and coeffs_all must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const size_t B = h->B, N = h->N, n = N + 3 * (N - 1), S = h->prm.S;
+    const size_t nx = B * n * 8, nf = B * 8, ni = B * 4, cnt = B * N * 3 * 2 * S, nc = cnt * 8, nt = B * N * 8;
+    if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_f, nf)) || (rc = ensure(h, h->b_status, ni)) ||
+        (rc = ensure(h, h->b_iters, ni)) || (rc = ensure(h, h->b_evals, ni)) || (rc = ensure(h, h->b_coeffs, nc)) ||
+        (rc = ensure(h, h->b_T, nt)) || (rc = ensure(h, h->b_gather, nc * h->nranks)))
+        return rc;
+    CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
+    // every rank must reach the collective, also when the parameter check short-circuits
+    CU(h, cudaMemsetAsync(h->b_coeffs.p, 0, nc, h->stream));
+    rc = mincob_optimize_device(h, (double *)h->b_x.p, (double *)h->b_f.p, (int32_t *)h->b_status.p,
+                                (int32_t *)h->b_iters.p, (int32_t *)h->b_evals.p, (double *)h->b_coeffs.p,
+                                T ? (double *)h->b_T.p : nullptr);
+    if (rc) return rc;
+    const bool ran = h->timed;
+    if ((rc = mincob_allgather_device(h, (const double *)h->b_coeffs.p, (double *)h->b_gather.p, (int64_t)cnt))) return rc;
+    if (ran) CU(h, cudaMemcpyAsync(x, h->b_x.p, nx, cudaMemcpyDeviceToHost, h->stream));
+    if (f && ran) CU(h, cudaMemcpyAsync(f, h->b_f.p, nf, cudaMemcpyDeviceToHost, h->stream));
+    if (status) CU(h, cudaMemcpyAsync(status, h->b_status.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    if (iters && ran) CU(h, cudaMemcpyAsync(iters, h->b_iters.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    if (evals && ran) CU(h, cudaMemcpyAsync(evals, h->b_evals.p, ni, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(coeffs_all, h->b_gather.p, nc * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    if (T && ran) CU(h, cudaMemcpyAsync(T, h->b_T.p, nt, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mincob_host_alloc(void **out, uint64_t bytes) {
+    if (!out) return MINCOB_E_INVALID;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? (size_t)bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : MINCOB_E_ALLOC;
+}
+int mincob_host_free(void *p) {
+    if (!p) return 0;
+    return cudaFreeHost(p) == cudaSuccess ? 0 : MINCOB_E_CUDA;
 }
 
 int mincob_comm_destroy(mincob_handle h) {

@@ -133,6 +133,17 @@ int mincob_nccl_unique_id(void *unique_id_128);
 int mincob_comm_init(mincob_handle h, int nranks, int rank, const void *unique_id_128);
 int mincob_allgather_device(mincob_handle h, const double *send_d, double *recv_d, int64_t count_per_rank);
 int mincob_comm_destroy(mincob_handle h);
+/*      HOST-pointer form of the sharded job (BASELINE.json config 5): optimize this rank's B problems
+ *      (as mincob_optimize), all-gather the Trajectory-order coefficients of every rank, and copy
+ *      them to coeffs_all [nranks*B][N][3][2S] (rank-major).  Without mincob_comm_init (one rank)
+ *      it is mincob_optimize.  Every rank must call it with the same B. */
+int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters,
+                            int32_t *evals, double *coeffs_all, double *T);
+
+/* ---- pinned host memory for the host-pointer entry points (cudaHostAlloc / cudaFreeHost), so a
+ *      C++ caller such as LearningPlanner needs no CUDA headers of its own. */
+int mincob_host_alloc(void **out, uint64_t bytes);
+int mincob_host_free(void *p);
 
 #ifdef __cplusplus
 }

@@ -207,6 +207,36 @@ int orc_optimize_batch(const orc_params *p, int B, int N, const double *head, co
     return 0;
 }
 
+// Same as orc_optimize_batch but the L-BFGS driver is passed in: either orc_lbfgs_optimize (the
+// restatement) or ref_lbfgs_optimize from oracle/_ref (the reference's own lbfgs.hpp, verbatim).
+typedef int (*lbfgs_driver_fn)(int n, double *x, double *f, orc::eval_fn eval, void *inst, const orc_params *p,
+                               int *iters, int *evals);
+int orc_optimize_batch_with(lbfgs_driver_fn driver, const orc_params *p, int B, int N, const double *head,
+                            const double *tail, const double *hpolys, const int *hrows, int K, double *x, double *f,
+                            int *status, int *iters, int *evals, double *coeffs, double *T, int nthreads) {
+    const int S = p->S, n = N + 3 * (N - 1);
+    if ((S != 3 && S != 4) || !driver) return -1;
+    run_threads(B, nthreads, [&](int lo, int hi) {
+        for (int b = lo; b < hi; ++b) {
+            CostBase *c = make_cost(*p, N, head + (size_t)b * 3 * S, tail + (size_t)b * 3 * S,
+                                    hpolys ? hpolys + (size_t)b * N * K * 4 : nullptr,
+                                    hrows ? hrows + (size_t)b * N : nullptr, K);
+            double fb = 0.0;
+            int it = 0, ev = 0;
+            const int ret = driver(n, x + (size_t)b * n, &fb, cost_thunk, c, p, &it, &ev);
+            if (f) f[b] = fb;
+            if (status) status[b] = ret;
+            if (iters) iters[b] = it;
+            if (evals) evals[b] = ev;
+            if (coeffs || T)
+                c->flat(x + (size_t)b * n, coeffs ? coeffs + (size_t)b * N * 3 * 2 * S : nullptr,
+                        T ? T + (size_t)b * N : nullptr);
+            delete c;
+        }
+    });
+    return 0;
+}
+
 int orc_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

@@ -117,6 +117,29 @@ class Oracle:
         assert rc == 0
         return dict(x=x, f=f, status=status, iters=iters, evals=evals, coeffs=coeffs, T=T)
 
+    def optimize_batch_ref(self, params, pb, x0=None, nthreads=1):
+        """optimize_batch with the L-BFGS driver of oracle/_ref (the reference's lbfgs.hpp compiled verbatim)
+        around the restated MINCO cost functional.  Falls back to the restated driver if _ref is absent."""
+        if self.ref is None:
+            out = self.optimize_batch(params, pb, x0, nthreads)
+            out["driver"] = "oracle/lbfgs_oracle.hpp (restated)"
+            return out
+        x = _f64(pb.x0() if x0 is None else x0).copy(); B, n = x.shape
+        S, N = params.S, pb.N
+        f = np.zeros(B); status = np.zeros(B, np.int32); iters = np.zeros(B, np.int32)
+        evals = np.zeros(B, np.int32); coeffs = np.zeros((B, N, 3, 2 * S)); T = np.zeros((B, N))
+        hp = pb.hpolys if pb.K > 0 else None
+        drv = C.cast(self.ref.ref_lbfgs_optimize, C.c_void_p)
+        fn = self.lib.orc_optimize_batch_with
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _dp, _dp, _ip, _ip, _ip,
+                       _dp, _dp, C.c_int]
+        rc = fn(drv, C.cast(C.byref(params), C.c_void_p), B, N, _ptr(pb.head), _ptr(pb.tail), _ptr(hp),
+                _ptr(pb.hrows, _ip), pb.K, _ptr(x), _ptr(f), _ptr(status, _ip), _ptr(iters, _ip), _ptr(evals, _ip),
+                _ptr(coeffs), _ptr(T), nthreads)
+        assert rc == 0
+        return dict(x=x, f=f, status=status, iters=iters, evals=evals, coeffs=coeffs, T=T,
+                    driver="oracle/_ref (reference gcopter/lbfgs.hpp, verbatim)")
+
     def hardware_threads(self):
         return int(self.lib.orc_hardware_threads())
 
