@@ -19,7 +19,8 @@ import numpy as np
 from .params import MincobParams, default_params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmincob.so")
+# MINCOB_LIBRARY selects another build of the same library (kernel A/B experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("MINCOB_LIBRARY") or os.path.join(_HERE, "libmincob.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _vp = C.c_void_p

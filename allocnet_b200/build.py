@@ -13,11 +13,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libmincob.so")
+OBJ = os.environ.get("MINCOB_BUILD_DIR") or os.path.join(HERE, "build")
+LIB = os.environ.get("MINCOB_BUILD_OUT") or os.path.join(HERE, "libmincob.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 INST = [(S, L) for S in (3, 4) for L in (8, 16, 32)]
+# resident blocks per SM the optimize kernel is compiled for (caps registers per thread); override for
+# experiments with MINCOB_MINB3 / MINCOB_MINB4 in the environment
+MINB = {3: int(os.environ.get("MINCOB_MINB3", "2")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
 
 
 def _nvcc():
@@ -55,7 +58,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     for S, L in INST:
         o = os.path.join(OBJ, f"kernels_s{S}_l{L}.o")
-        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", "-c",
+        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={MINB.get(S, 2)}", "-c",
                       os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
     o = os.path.join(OBJ, "mincob.o")
     jobs.append(([nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))

@@ -50,6 +50,9 @@ struct BatchArgs {
     double *x, *coeffs, *T;
     int *status, *iters, *evals;
     int *counter;               // work queue head
+    double *hist;               // optimize: (s, y) history scratch, one slab per resident group
+    double *mult;               // optimize: PCR multiplier scratch, one slab per resident block
+    int planes_in_smem;         // optimize: stage each problem's half-planes in shared memory
     unsigned long long *total_evals;  // optional: sum of evaluations (for the roofline numerator)
 };
 

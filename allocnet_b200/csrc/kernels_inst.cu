@@ -19,7 +19,7 @@ template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int propagate) {
     constexpr int D = 2 * S, b = S - 1;
     const int lig = (threadIdx.x & 31) % LPT;
-    const unsigned mask = group_mask<LPT>();
+    const unsigned mask = 0xffffffffu;  // uniform control flow: whole warp participates in every shuffle
     const int N = a.N;
     const int groups = gridDim.x * (THREADS / LPT);
     const int rounds = (a.B + groups - 1) / groups;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int p
                 td[d][x] = (lig == Ne - 1) ? tail[(d + 1) * 3 + x] : 0.0;
             }
         const double T = active ? a.ts[(size_t)pp * N + lig] : 1.0;
-        Spline<S, LPT> sp;
+        SplineReg<S, LPT> sp;
         double chat[D][3];
         spline_solve<S, LPT>(mask, lig, Ne, T, P0, P1, hd, td, sp, chat);
         if (!propagate) {
@@ -101,22 +101,65 @@ LaunchResult launch_evaluate(cudaStream_t st, int sm_count, const DevParams &dp,
     return ok(cudaGetLastError());
 }
 
-LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp, const BatchArgs &a) {
-    const int m = dp.mem, past = dp.past > 0 ? dp.past : 1;
-    const size_t smem = (size_t)GPB * (2 * m * 4 * LPT + 2 * m + past) * sizeof(double);
-    auto kern = optimize_kernel<S, LPT, THREADS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return LaunchResult{cudaSuccess, MINCOB_E_INVALID, smem};
+// Shared memory per block and grid of the persistent optimize kernel.  Half-planes are staged in
+// shared memory when at least MINCOB_MINB blocks per SM still fit; otherwise they are read from global.
+struct OptPlan {
+    int psmem, blocks;
+    size_t smem, hist_bytes, mult_bytes;
+    int code;
+    cudaError_t err;
+};
+template <bool PSMEM>
+static int blocks_per_sm(size_t smem, cudaError_t &e) {
+    auto kern = optimize_kernel<S, LPT, THREADS, PSMEM>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { e = cudaSuccess; (void)cudaGetLastError(); return 0; }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    if (e != cudaSuccess) return ok(e);
-    if (per_sm < 1) return LaunchResult{cudaSuccess, MINCOB_E_INVALID, smem};
-    int blocks = per_sm * sm_count;
+    return e == cudaSuccess ? per_sm : 0;
+}
+static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs &a) {
+    OptPlan pl{0, 0, 0, 0, 0, 0, cudaSuccess};
+    const bool have = a.hpolys && a.hrows && a.K > 0;
+    int per_sm = 0;
+    if (have && dp.penalties) {
+        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 1) * sizeof(double);
+        per_sm = blocks_per_sm<true>(pl.smem, pl.err);
+        if (pl.err != cudaSuccess) return pl;
+        pl.psmem = per_sm >= MINCOB_MINB || per_sm >= 2;
+    }
+    if (!pl.psmem) {
+        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0) * sizeof(double);
+        per_sm = blocks_per_sm<false>(pl.smem, pl.err);
+        if (pl.err != cudaSuccess) return pl;
+    }
+    if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
+    pl.blocks = per_sm * sm_count;
     const int need = (a.B + GPB - 1) / GPB;
-    if (blocks > need) blocks = need;
+    if (pl.blocks > need) pl.blocks = need;
+    pl.hist_bytes = (size_t)pl.blocks * GPB * dp.mem * LPT * 8 * sizeof(double);
+    pl.hist_bytes = (pl.hist_bytes + 255) & ~(size_t)255;
+    pl.mult_bytes = (size_t)pl.blocks * SplineReg<S, LPT>::NM * THREADS * sizeof(double);
+    return pl;
+}
+
+// one allocation: [history slabs | multiplier slabs]
+size_t optimize_scratch(int sm_count, const DevParams &dp, const BatchArgs &a) {
+    const OptPlan pl = plan_optimize(sm_count, dp, a);
+    return pl.hist_bytes + pl.mult_bytes;
+}
+
+LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp, const BatchArgs &a) {
+    const OptPlan pl = plan_optimize(sm_count, dp, a);
+    if (pl.err != cudaSuccess) return ok(pl.err);
+    if (pl.code) return LaunchResult{cudaSuccess, pl.code, pl.smem};
+    cudaError_t e;
     if ((e = cudaMemsetAsync(a.counter, 0, sizeof(int), st)) != cudaSuccess) return ok(e);
     if ((e = cudaMemsetAsync(a.total_evals, 0, sizeof(unsigned long long), st)) != cudaSuccess) return ok(e);
-    kern<<<blocks, THREADS, smem, st>>>(dp, a);
+    BatchArgs b = a;
+    b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
+    if (pl.psmem) optimize_kernel<S, LPT, THREADS, true><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    else optimize_kernel<S, LPT, THREADS, false><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
     return ok(cudaGetLastError());
 }
 
@@ -128,7 +171,7 @@ LaunchResult launch_minco(cudaStream_t st, int sm_count, const MincoArgs &a, int
     return ok(cudaGetLastError());
 }
 
-const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco};
+const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco, optimize_scratch};
 }  // namespace
 
 #define MINCOB_CAT_(a, b, c) mincob_table_##a##_##b

@@ -14,6 +14,8 @@ struct LaunchTable {
     LaunchResult (*evaluate)(cudaStream_t, int sm_count, const DevParams &, const BatchArgs &);
     LaunchResult (*optimize)(cudaStream_t, int sm_count, const DevParams &, const BatchArgs &);
     LaunchResult (*minco)(cudaStream_t, int sm_count, const MincoArgs &, int propagate);
+    // bytes of global scratch (L-BFGS history slabs) `optimize` needs in BatchArgs::hist
+    size_t (*optimize_scratch)(int sm_count, const DevParams &, const BatchArgs &);
 };
 }  // namespace mincob
 const mincob::LaunchTable *mincob_table_3_8();

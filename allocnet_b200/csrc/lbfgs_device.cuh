@@ -15,18 +15,25 @@
 #pragma once
 #include "minco_device.cuh"
 
+#ifndef MINCOB_MINB
+#define MINCOB_MINB 2   // resident blocks per SM the optimize kernel is compiled for (register cap)
+#endif
+
 namespace mincob {
 
 
 
+// problem p as it lies in global memory (C-ABI layout of include/mincob.h)
 template <int S>
-__device__ __forceinline__ ProblemView view_of(const BatchArgs &a, int p) {
+__device__ __forceinline__ ProblemView view_global(const BatchArgs &a, int p, int lig) {
     ProblemView pv;
     pv.head = a.head + (size_t)p * S * 3;
     pv.tail = a.tail + (size_t)p * S * 3;
-    pv.planes = a.hpolys ? a.hpolys + (size_t)p * a.N * a.K * 4 : nullptr;
-    pv.hrows = a.hrows ? a.hrows + (size_t)p * a.N : nullptr;
-    pv.K = a.hpolys ? a.K : 0;
+    const bool have = a.hpolys && a.hrows && a.K > 0;
+    const int l = lig < a.N ? lig : 0;
+    pv.planes = have ? a.hpolys + ((size_t)p * a.N + l) * a.K * 4 : nullptr;
+    pv.rstride = 4;
+    pv.rows = have ? min(a.hrows[(size_t)p * a.N + l], a.K) : 0;
     return pv;
 }
 
@@ -56,9 +63,10 @@ __device__ __forceinline__ double ginf(unsigned m, const double (&a)[4]) {
 
 // setParameters + getTrajectory at x: writes Trajectory-order coefficients and durations.
 template <int S, int LPT>
-__device__ __noinline__ void emit_trajectory(unsigned mask, int lig, int N, const ProblemView pv,
+__device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, const ProblemView &pv,
                                              const double (&xv)[4], double *coeffs, double *Tout) {
     constexpr int D = 2 * S, b = S - 1;
+    constexpr unsigned mask = 0xffffffffu;  // called by whole warps only
     const bool active = lig < N;
     double P0[3], P1[3], hd[b][3], td[b][3];
 #pragma unroll
@@ -75,7 +83,7 @@ __device__ __noinline__ void emit_trajectory(unsigned mask, int lig, int N, cons
             td[a][x] = (lig == N - 1) ? pv.tail[(a + 1) * 3 + x] : 0.0;
         }
     const double T = active ? forward_t(xv[0]) : 1.0;
-    Spline<S, LPT> sp;
+    SplineReg<S, LPT> sp;
     double chat[D][3];
     spline_solve<S, LPT>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
     if (active) {
@@ -92,24 +100,49 @@ __device__ __noinline__ void emit_trajectory(unsigned mask, int lig, int N, cons
 
 enum { PH_FETCH = 0, PH_FIRST = 1, PH_LS = 2, PH_IDLE = 3 };
 
-template <int S, int LPT, int THREADS>
-__global__ void __launch_bounds__(THREADS) optimize_kernel(const DevParams P, const BatchArgs a) {
-    constexpr int GPB = THREADS / LPT;
+// doubles of shared memory one group needs (host and device must agree)
+__host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m, int past, int planes_in_smem) {
+    const int planes = planes_in_smem ? N * K * 4 : 0;
+    int small = 2 * S * 3 + 2 * m + (past > 0 ? past : 1);
+    small = (small + 3) & ~3;                      // keep every group's plane stage 32-byte aligned
+    return planes + small;
+}
+
+// Control flow of one trip (all 32 lanes of the warp walk it together; the 32/LPT groups differ only
+// in predicates, so every shuffle uses the full mask and no branch encloses a shuffle):
+//   fetch (+ stage the problem in shared memory) -> costFunctional -> reductions -> per-group scalar
+//   decisions (lbfgs.hpp tests, in the reference's order) -> history update + two-loop recursion ->
+//   line-search entry -> retire.
+// Memory: x, g, xp, gp, d in registers (lane i owns tau_i and q_i).  Shared memory per group: the
+// problem's half-planes, transposed to plane-major so that one row index is one conflict-free
+// 32*N-byte read for the group (they are read 3x17x16 times per evaluation, ~400 evaluations per
+// problem), head/tail states, alpha / y.s / past-f rings.  The (s, y) history (touched once per
+// iteration) lives in a global scratch slab per resident group, which stays in L2.
+template <int S, int LPT, int THREADS, bool PSMEM>
+__global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const DevParams P, const BatchArgs a) {
+    constexpr unsigned FULL = 0xffffffffu;
     const int lig = (threadIdx.x & 31) % LPT;
     const int gib = threadIdx.x / LPT;
-    const unsigned mask = group_mask<LPT>();
-    const int N = a.N, n = N + 3 * (N - 1), m = P.mem, past = P.past;
+    const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = P.mem, past = P.past;
 
-    extern __shared__ double smem[];
-    const int per_group = 2 * m * 4 * LPT + 2 * m + (past > 0 ? past : 1);
-    double *hs = smem + (size_t)gib * per_group;
-    double *hy = hs + m * 4 * LPT;
-    double *alpha = hy + m * 4 * LPT;
+    extern __shared__ __align__(32) double smem[];
+    double *grp = smem + (size_t)gib * optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0);
+    double *planes_s = grp;                                  // [K][N][4] when PSMEM
+    double *ht = grp + (PSMEM ? N * K * 4 : 0);              // head [S][3], tail [S][3]
+    double *alpha = ht + 2 * S * 3;
     double *ysv = alpha + m;
     double *pf = ysv + m;
-    (void)GPB;
+    // history slab of this group: [m][LPT][8] = (s0..s3, y0..y3) of lane lig in slot j
+    double *hist = a.hist + ((size_t)blockIdx.x * (THREADS / LPT) + gib) * ((size_t)m * LPT * 8) + (size_t)lig * 8;
+
+    // PCR multipliers of the current evaluation: slot i of thread t at mult[(block*NM + i)*THREADS + t]
+    GlobalStore mstore;
+    mstore.p = a.mult + (size_t)blockIdx.x * SplineReg<S, LPT>::NM * THREADS + threadIdx.x;
+    mstore.stride = THREADS;
 
     int phase = PH_FETCH, prob = 0;
+    ProblemView pv;
+    pv.head = ht; pv.tail = ht + S * 3; pv.planes = nullptr; pv.rstride = 4; pv.rows = 0;
     double x[4] = {0, 0, 0, 0}, g[4], xp[4] = {0, 0, 0, 0}, gp[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
     double fx = 0.0, stp = 0.0, finit = 0.0, dgtest = 0.0, dstest = 0.0, lo = 0.0, hi = 0.0;
     int count = 0, k = 0, end = 0, bound = 0, evals = 0;
@@ -117,49 +150,77 @@ __global__ void __launch_bounds__(THREADS) optimize_kernel(const DevParams P, co
     unsigned long long my_evals = 0ull;
 
     for (;;) {
-        if (phase == PH_FETCH) {
+        // ---- fetch ---------------------------------------------------------------------------
+        if (__any_sync(FULL, phase == PH_FETCH)) {
+            const bool want = phase == PH_FETCH;
             int p = 0;
-            if (lig == 0) p = atomicAdd(a.counter, 1);
-            p = __shfl_sync(mask, p, 0, LPT);
-            if (p >= a.B) {
-                phase = PH_IDLE;
-                prob = 0;
-            } else {
-                prob = p;
-                load_x<LPT>(a.x + (size_t)p * n, N, lig, x);
-                phase = PH_FIRST;
+            if (want && lig == 0) p = atomicAdd(a.counter, 1);
+            p = __shfl_sync(FULL, p, 0, LPT);
+            if (want) {
+                if (p >= a.B) {
+                    phase = PH_IDLE; prob = 0;
+                    for (int i = lig; i < 2 * S * 3; i += LPT) ht[i] = 0.0;
+                    pv.planes = nullptr; pv.rows = 0;
+                } else {
+                    prob = p;
+                    load_x<LPT>(a.x + (size_t)p * n, N, lig, x);
+                    phase = PH_FIRST;
+                    for (int i = lig; i < 2 * S * 3; i += LPT)
+                        ht[i] = i < S * 3 ? a.head[(size_t)p * S * 3 + i] : a.tail[(size_t)p * S * 3 + i - S * 3];
+                    const bool have = a.hpolys && a.hrows && K > 0;
+                    pv.rows = (have && lig < N) ? min(a.hrows[(size_t)p * N + lig], K) : 0;
+                    if (PSMEM) {
+                        // [N][K][4] (global, one contiguous 32*N*K-byte block) -> [K][N][4] (shared)
+                        const double2 *src = reinterpret_cast<const double2 *>(a.hpolys + (size_t)p * N * K * 4);
+                        double2 *dst = reinterpret_cast<double2 *>(planes_s);
+                        for (int r = lig; r < N * K; r += LPT) {
+                            const int piece = r / K, kk = r - piece * K;
+                            const double2 lo2 = __ldg(src + 2 * r), hi2 = __ldg(src + 2 * r + 1);
+                            dst[2 * (kk * N + piece)] = lo2;
+                            dst[2 * (kk * N + piece) + 1] = hi2;
+                        }
+                        pv.planes = have ? planes_s + (lig < N ? lig : 0) * 4 : nullptr;
+                        pv.rstride = 4 * N;
+                    } else {
+                        pv.planes = have ? a.hpolys + ((size_t)p * N + (lig < N ? lig : 0)) * K * 4 : nullptr;
+                        pv.rstride = 4;
+                    }
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-        if (__all_sync(0xffffffffu, phase == PH_IDLE)) break;
+        if (__all_sync(FULL, phase == PH_IDLE)) break;
 
-        const ProblemView pv = view_of<S>(a, prob);
+        // ---- costFunctional --------------------------------------------------------------------
         double xq[3] = {x[1], x[2], x[3]}, gq[3];
-        const double f = cost_functional<S, LPT>(P, mask, lig, phase == PH_IDLE ? 0 : N, pv, x[0], xq, g[0], gq);
+        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, pv, mstore, x[0], xq, g[0], gq);
         g[1] = gq[0]; g[2] = gq[1]; g[3] = gq[2];
 
-        if (phase == PH_IDLE) continue;
+        // ---- reductions every group may need ------------------------------------------------------
+        const double gn = ginf<LPT>(FULL, g), xn = ginf<LPT>(FULL, x);
+        const double gg = gdot<LPT>(FULL, g, g);
+        const double gd = gdot<LPT>(FULL, g, d);
+        const double pfk = (past > 0) ? pf[k % past] : 0.0;
+        __syncwarp();
 
-        int finish = 0, ret = 0;     // finish: 1 = done with this problem
-        bool start_ls = false;
-        if (phase == PH_FIRST) {
+        // ---- per-group scalar decisions (no shuffles below until the next section) -------------
+        int finish = 0, ret = 0;
+        bool start_ls = false, upd = false, write_pf = false;
+        if (phase == PH_FIRST) {            // lbfgs.hpp:518-545
             evals = 1;
             fx = f;
-            if (lig == 0) pf[0] = fx;
-            __syncwarp(mask);
+            write_pf = true;
+            k = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] = -g[i];
-            const double gn = ginf<LPT>(mask, g), xn = ginf<LPT>(mask, x);
-            k = 0;
             if (gn / fmax(1.0, xn) < P.g_eps) {
-                ret = LBFGS_CONVERGENCE;
-                finish = 1;
+                ret = LBFGS_CONVERGENCE; finish = 1;
             } else {
-                stp = 1.0 / sqrt(gdot<LPT>(mask, d, d));
+                stp = 1.0 / sqrt(gg);
                 k = 1; end = 0; bound = 0;
                 start_ls = true;
             }
-        } else {  // PH_LS: one trial point of line_search_lewisoverton evaluated
+        } else if (phase == PH_LS) {        // one trial point of line_search_lewisoverton (:311-384)
             ++count; ++evals;
             fx = f;
             int fail = 0;
@@ -168,7 +229,7 @@ __global__ void __launch_bounds__(THREADS) optimize_kernel(const DevParams P, co
                 fail = LBFGSERR_INVALID_FUNCVAL;
             } else if (f > finit + stp * dgtest) {
                 hi = stp; bracketed = true;
-            } else if (gdot<LPT>(mask, g, d) < dstest) {
+            } else if (gd < dstest) {
                 lo = stp;
             } else {
                 done = true;
@@ -189,113 +250,126 @@ __global__ void __launch_bounds__(THREADS) optimize_kernel(const DevParams P, co
                     for (int i = 0; i < 4; ++i) x[i] = xp[i] + stp * d[i];
                 }
             }
-            if (fail) {  // lbfgs.hpp:570-577: revert to the last good iterate
+            if (fail) {                     // lbfgs.hpp:570-577: revert to the last good iterate
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { x[i] = xp[i]; g[i] = gp[i]; }
-                ret = fail;
-                finish = 1;
-            } else if (done) {
-                const double gn = ginf<LPT>(mask, g), xn = ginf<LPT>(mask, x);
-                if (gn / fmax(1.0, xn) < P.g_eps) {
-                    ret = LBFGS_CONVERGENCE; finish = 1;
-                }
+                ret = fail; finish = 1;
+            } else if (done) {              // lbfgs.hpp:580-640
+                if (gn / fmax(1.0, xn) < P.g_eps) { ret = LBFGS_CONVERGENCE; finish = 1; }
                 if (!finish && past > 0) {
-                    if (past <= k) {
-                        const double rate = fabs(pf[k % past] - fx) / fmax(1.0, fabs(fx));
-                        if (rate < P.delta) { ret = LBFGS_STOP; finish = 1; }
-                    }
-                    if (!finish) {
-                        __syncwarp(mask);
-                        if (lig == 0) pf[k % past] = fx;
-                        __syncwarp(mask);
-                    }
+                    if (past <= k && fabs(pfk - fx) / fmax(1.0, fabs(fx)) < P.delta) { ret = LBFGS_STOP; finish = 1; }
+                    if (!finish) write_pf = true;
                 }
                 if (!finish && P.max_iter != 0 && P.max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; finish = 1; }
-                if (!finish) {
-                    ++k;
-                    double sv[4], yv[4];
+                if (!finish) upd = true;
+            }
+        }
+        if (write_pf && lig == 0) pf[past > 0 ? k % past : 0] = fx;
+
+        // ---- new iterate: (s, y) pair, cautious update, two-loop recursion (lbfgs.hpp:642-709) ----
+        if (__any_sync(FULL, upd)) {
+            double sv[4], yv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        sv[i] = x[i] - xp[i]; yv[i] = g[i] - gp[i];
-                        hs[(end * 4 + i) * LPT + lig] = sv[i];
-                        hy[(end * 4 + i) * LPT + lig] = yv[i];
-                    }
-                    const double ys = gdot<LPT>(mask, yv, sv), yy = gdot<LPT>(mask, yv, yv);
-                    if (lig == 0) ysv[end] = ys;
-                    __syncwarp(mask);
+            for (int i = 0; i < 4; ++i) { sv[i] = x[i] - xp[i]; yv[i] = g[i] - gp[i]; }
+            const double ys = gdot<LPT>(FULL, yv, sv), yy = gdot<LPT>(FULL, yv, yv);
+            const double ss = gdot<LPT>(FULL, sv, sv), gpgp = gdot<LPT>(FULL, gp, gp);
+            bool two = false;
+            if (upd) {
+                ++k;
+                double4 *slot = reinterpret_cast<double4 *>(hist + (size_t)end * LPT * 8);
+                slot[0] = make_double4(sv[0], sv[1], sv[2], sv[3]);
+                slot[1] = make_double4(yv[0], yv[1], yv[2], yv[3]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) d[i] = -g[i];
-                    const double cau = gdot<LPT>(mask, sv, sv) * sqrt(gdot<LPT>(mask, gp, gp)) * P.cautious;
-                    if (ys > cau) {
-                        ++bound;
-                        bound = m < bound ? m : bound;
-                        end = (end + 1) % m;
-                        int j = end;
-                        for (int i = 0; i < bound; ++i) {
-                            j = (j + m - 1) % m;
-                            double sj[4], yj[4];
+                for (int i = 0; i < 4; ++i) d[i] = -g[i];
+                if (lig == 0) ysv[end] = ys;
+                two = ys > ss * sqrt(gpgp) * P.cautious;
+                if (two) {
+                    ++bound;
+                    bound = m < bound ? m : bound;
+                    end = (end + 1 == m) ? 0 : end + 1;
+                }
+                stp = 1.0;
+                start_ls = true;
+            }
+            __syncwarp();
+            const int nb = __reduce_max_sync(FULL, two ? bound : 0);
+            int j = end;
+#pragma unroll 1
+            for (int i = 0; i < nb; ++i) {
+                const bool on = two && i < bound;
+                if (on) j = (j == 0 ? m : j) - 1;
+                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
+                const double4 s4 = slot[0], y4 = slot[1];
+                const double sj[4] = {s4.x, s4.y, s4.z, s4.w};
+                const double aj = gdot<LPT>(FULL, sj, d) / ysv[j];
+                if (on) {
+                    if (lig == 0) alpha[j] = aj;
+                    d[0] -= aj * y4.x; d[1] -= aj * y4.y; d[2] -= aj * y4.z; d[3] -= aj * y4.w;
+                }
+            }
+            __syncwarp();
+            if (two) {
+                const double sc0 = ys / yy;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) { sj[u] = hs[(j * 4 + u) * LPT + lig]; yj[u] = hy[(j * 4 + u) * LPT + lig]; }
-                            const double aj = gdot<LPT>(mask, sj, d) / ysv[j];
-                            if (lig == 0) alpha[j] = aj;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) d[u] += (-aj) * yj[u];
-                        }
-                        __syncwarp(mask);
-                        const double sc0 = ys / yy;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) d[u] *= sc0;
-                        for (int i = 0; i < bound; ++i) {
-                            double sj[4], yj[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) { sj[u] = hs[(j * 4 + u) * LPT + lig]; yj[u] = hy[(j * 4 + u) * LPT + lig]; }
-                            const double beta = gdot<LPT>(mask, yj, d) / ysv[j];
-                            const double cf = alpha[j] - beta;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) d[u] += cf * sj[u];
-                            j = (j + 1) % m;
-                        }
-                    }
-                    stp = 1.0;
-                    start_ls = true;
+                for (int u = 0; u < 4; ++u) d[u] *= sc0;
+            }
+#pragma unroll 1
+            for (int i = 0; i < nb; ++i) {
+                const bool on = two && i < bound;
+                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
+                const double4 s4 = slot[0], y4 = slot[1];
+                const double yj[4] = {y4.x, y4.y, y4.z, y4.w};
+                const double beta = gdot<LPT>(FULL, yj, d) / ysv[j];
+                if (on) {
+                    const double cf = alpha[j] - beta;
+                    d[0] += cf * s4.x; d[1] += cf * s4.y; d[2] += cf * s4.z; d[3] += cf * s4.w;
+                    j = (j + 1 == m) ? 0 : j + 1;
                 }
             }
         }
-        if (start_ls) {  // entry of line_search_lewisoverton (lbfgs.hpp:276-310)
+
+        // ---- entry of line_search_lewisoverton (lbfgs.hpp:276-310) -------------------------------
+        if (__any_sync(FULL, start_ls)) {
+            if (start_ls) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { xp[i] = x[i]; gp[i] = g[i]; }
-            int fail = 0;
-            double dginit = 0.0;
-            if (!(stp > 0.0)) fail = LBFGSERR_INVALIDPARAMETERS;
-            else {
-                dginit = gdot<LPT>(mask, gp, d);
-                if (0.0 < dginit) fail = LBFGSERR_INCREASEGRADIENT;
+                for (int i = 0; i < 4; ++i) { xp[i] = x[i]; gp[i] = g[i]; }
             }
-            if (fail) {
-                ret = fail; finish = 1;
-            } else {
-                finit = fx;
-                dgtest = P.f_dec * dginit;
-                dstest = P.s_curv * dginit;
-                count = 0; bracketed = false; touched = false; lo = 0.0; hi = P.max_step;
+            const double dginit = gdot<LPT>(FULL, gp, d);
+            if (start_ls) {
+                int fail = 0;
+                if (!(stp > 0.0)) fail = LBFGSERR_INVALIDPARAMETERS;
+                else if (0.0 < dginit) fail = LBFGSERR_INCREASEGRADIENT;
+                if (fail) {
+                    ret = fail; finish = 1;
+                } else {
+                    finit = fx;
+                    dgtest = P.f_dec * dginit;
+                    dstest = P.s_curv * dginit;
+                    count = 0; bracketed = false; touched = false; lo = 0.0; hi = P.max_step;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) x[i] = xp[i] + stp * d[i];
-                phase = PH_LS;
+                    for (int i = 0; i < 4; ++i) x[i] = xp[i] + stp * d[i];
+                    phase = PH_LS;
+                }
             }
         }
-        if (finish) {
-            store_x<LPT>(a.x + (size_t)prob * n, N, lig, x);
-            if (lig == 0) {
-                if (a.f_out) a.f_out[prob] = fx;
-                if (a.status) a.status[prob] = ret;
-                if (a.iters) a.iters[prob] = k;
-                if (a.evals) a.evals[prob] = evals;
-                my_evals += (unsigned long long)evals;
+
+        // ---- retire ----------------------------------------------------------------------------
+        if (__any_sync(FULL, finish != 0)) {
+            if (finish) {
+                store_x<LPT>(a.x + (size_t)prob * n, N, lig, x);
+                if (lig == 0) {
+                    if (a.f_out) a.f_out[prob] = fx;
+                    if (a.status) a.status[prob] = ret;
+                    if (a.iters) a.iters[prob] = k;
+                    if (a.evals) a.evals[prob] = evals;
+                    my_evals += (unsigned long long)evals;
+                }
             }
             if (a.coeffs || a.T)
-                emit_trajectory<S, LPT>(mask, lig, N, pv, x, a.coeffs ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
-                                        a.T ? a.T + (size_t)prob * N : nullptr);
-            phase = PH_FETCH;
+                emit_trajectory<S, LPT>(FULL, lig, finish ? N : 0, pv, x,
+                                        (finish && a.coeffs) ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
+                                        (finish && a.T) ? a.T + (size_t)prob * N : nullptr);
+            if (finish) phase = PH_FETCH;
         }
     }
     if (a.total_evals && my_evals) atomicAdd(a.total_evals, my_evals);
@@ -305,7 +379,6 @@ __global__ void __launch_bounds__(THREADS) optimize_kernel(const DevParams P, co
 template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) evaluate_kernel(const DevParams P, const BatchArgs a) {
     const int lig = (threadIdx.x & 31) % LPT;
-    const unsigned mask = group_mask<LPT>();
     const int N = a.N, n = N + 3 * (N - 1);
     const int groups = gridDim.x * (THREADS / LPT);
     const int rounds = (a.B + groups - 1) / groups;
@@ -313,11 +386,11 @@ __global__ void __launch_bounds__(THREADS) evaluate_kernel(const DevParams P, co
     for (int it = 0; it < rounds; ++it, p += groups) {
         const bool live = p < a.B;
         const int pp = live ? p : 0;
-        const ProblemView pv = view_of<S>(a, pp);
+        const ProblemView pv = view_global<S>(a, pp, lig);
         double xv[4], gt, gq[3];
         load_x<LPT>(a.x_in + (size_t)pp * n, live ? N : 0, lig, xv);
         double xq[3] = {xv[1], xv[2], xv[3]};
-        const double f = cost_functional<S, LPT>(P, mask, lig, live ? N : 0, pv, xv[0], xq, gt, gq);
+        const double f = cost_functional<S, LPT, false>(P, 0xffffffffu, lig, live ? N : 0, pv, typename SplineReg<S, LPT>::ST_t(), xv[0], xq, gt, gq);
         if (live) {
             double gv[4] = {gt, gq[0], gq[1], gq[2]};
             store_x<LPT>(a.g_out + (size_t)p * n, N, lig, gv);

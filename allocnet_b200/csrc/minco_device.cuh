@@ -82,11 +82,12 @@ __device__ __forceinline__ double backward_grad_t(double tau, double gradT) {
     return gradT * (1.0 - tau) / (den * den);
 }
 // smoothedL1, gcopter/firi.hpp:60-84; caller guarantees x > 0.
-__device__ __forceinline__ void smoothed_l1_pos(double mu, double x, double &f, double &df) {
+// imu = 1/mu (hoisted: an fp64 division is ~30 instructions).
+__device__ __forceinline__ void smoothed_l1_pos(double mu, double imu, double x, double &f, double &df) {
     if (x > mu) { f = x - 0.5 * mu; df = 1.0; return; }
-    const double r = x / mu, r2 = r * r, h = mu - 0.5 * x;
+    const double r = x * imu, r2 = r * r, h = mu - 0.5 * x;
     f = h * r2 * r;
-    df = r2 * (-0.5 * r + 3.0 * h / mu);
+    df = r2 * (-0.5 * r + 3.0 * h * imu);
 }
 
 // ---- small dense helpers (b = S-1 = 2 or 3) ---------------------------------------------
@@ -113,22 +114,49 @@ __device__ __forceinline__ void inv_small<3>(const double (&d)[3][3], double (&o
     o[2][2] = (d[0][0] * d[1][1] - d[0][1] * d[1][0]) * r;
 }
 
-// Per-lane (= per-piece) spline state kept between the forward solve and the adjoint.
-template <int S, int LPT>
-struct Spline {
-    static constexpr int D = 2 * S, b = S - 1, LEVELS = Log2<LPT>::value;
-    double T, iT, t5;       // duration, 1/T, T^(1-2S)
-    double sh[D][3];        // scaled boundary states L*s: rows 0..S-1 start, S..2S-1 end (row S holds dP = P1-P0)
-    double c[D][3];         // monomial coefficients, ascending powers (row k = c_k)
-    double al[LEVELS][b][b], ga[LEVELS][b][b], Dinv[b][b];  // PCR multipliers of this block row
+// Where a lane keeps its PCR multipliers between setParameters and propogateGrad: NM doubles that
+// are written once and read once per evaluation.  RegStore holds them in registers (short kernels);
+// GlobalStore parks them in a lane-strided global slab (coalesced, L2-resident) so that they do not
+// occupy 2*NM registers across the penalty loop of the persistent optimize kernel.
+template <int NM>
+struct RegStore {
+    double v[NM];
+    __device__ __forceinline__ void put(int i, double x) { v[i] = x; }
+    __device__ __forceinline__ double get(int i) const { return v[i]; }
+};
+struct GlobalStore {
+    double *p;     // this lane's first slot
+    int stride;    // distance between slots (threads sharing the slab)
+    __device__ __forceinline__ void put(int i, double x) { __stcg(p + (size_t)i * stride, x); }
+    __device__ __forceinline__ double get(int i) const { return __ldcg(p + (size_t)i * stride); }
 };
 
-// PCR forward pass on the right-hand side only (uses the stored multipliers).
+// Per-lane (= per-piece) spline state kept between the forward solve and the adjoint.
+template <int S, int LPT, class ST>
+struct Spline {
+    static constexpr int D = 2 * S, b = S - 1, LEVELS = Log2<LPT>::value;
+    static constexpr int NM = (2 * LEVELS + 1) * b * b;   // al, ga per level + Dinv
+    double T, iT, t5;       // duration, 1/T, T^(1-2S)
+    double c[D][3];         // monomial coefficients, ascending powers (row k = c_k)
+    using ST_t = ST;
+    ST st;                  // PCR multipliers of this block row
+    static __device__ __forceinline__ constexpr int ial(int l, int a, int k) { return ((2 * l) * b + a) * b + k; }
+    static __device__ __forceinline__ constexpr int iga(int l, int a, int k) { return ((2 * l + 1) * b + a) * b + k; }
+    static __device__ __forceinline__ constexpr int idi(int a, int k) { return (2 * LEVELS * b + a) * b + k; }
+};
 template <int S, int LPT>
-__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S, LPT> &sp, double (&r)[S - 1][3]) {
+using SplineReg = Spline<S, LPT, RegStore<(2 * Log2<LPT>::value + 1) * (S - 1) * (S - 1)>>;
+
+// PCR forward pass on the right-hand side only (uses the stored multipliers).
+template <int S, int LPT, class ST>
+__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S, LPT, ST> &sp, double (&r)[S - 1][3]) {
     constexpr int b = S - 1;
+    using SP = Spline<S, LPT, ST>;
+    double mul[SP::NM];   // every multiplier of this lane, fetched up front (independent loads)
 #pragma unroll
-    for (int l = 0; l < Spline<S, LPT>::LEVELS; ++l) {
+    for (int i = 0; i < SP::NM; ++i) mul[i] = sp.st.get(i);
+#pragma unroll
+    for (int l = 0; l < SP::LEVELS; ++l) {
         const int s = 1 << l;
         double rm[b][3], rp[b][3];
 #pragma unroll
@@ -138,17 +166,14 @@ __device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S
                 rm[a][x] = sh_up<LPT>(mask, r[a][x], s);
                 rp[a][x] = sh_dn<LPT>(mask, r[a][x], s);
             }
-        const bool vm = lig >= s, vp = lig + s < LPT;
 #pragma unroll
         for (int a = 0; a < b; ++a)
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double acc = r[a][x];
 #pragma unroll
-                for (int k = 0; k < b; ++k) {
-                    if (vm) acc -= sp.al[l][a][k] * rm[k][x];
-                    if (vp) acc -= sp.ga[l][a][k] * rp[k][x];
-                }
+                for (int k = 0; k < b; ++k)   // al / ga are zero where the neighbour row does not exist
+                    acc = fma(-mul[SP::iga(l, a, k)], rp[k][x], fma(-mul[SP::ial(l, a, k)], rm[k][x], acc));
                 r[a][x] = acc;
             }
     }
@@ -159,7 +184,7 @@ __device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S
         for (int x = 0; x < 3; ++x) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < b; ++k) acc += sp.Dinv[a][k] * r[k][x];
+            for (int k = 0; k < b; ++k) acc += mul[SP::idi(a, k)] * r[k][x];
             y[a][x] = acc;
         }
 #pragma unroll
@@ -171,12 +196,13 @@ __device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S
 // setParameters: lane `lig` (< N active) holds piece lig with duration T, start position P0,
 // end position P1; hd/td are the head / tail derivatives 1..S-1 (used by lanes 0 / N-1).
 // Output: sp (coefficients + factorisation), chat (normalised coefficients c_k T^k).
-template <int S, int LPT>
+template <int S, int LPT, class ST>
 __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, double Tin, const double (&P0)[3],
                                              const double (&P1)[3], const double (&hd)[S - 1][3],
-                                             const double (&td)[S - 1][3], Spline<S, LPT> &sp,
+                                             const double (&td)[S - 1][3], Spline<S, LPT, ST> &sp,
                                              double (&chat)[2 * S][3]) {
     constexpr int D = 2 * S, b = S - 1;
+    using SP = Spline<S, LPT, ST>;
     using HK = HermiteK<S>;
     const bool active = lig < N;
     const double T = active ? Tin : 1.0;
@@ -245,7 +271,7 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
     }
     // parallel cyclic reduction
 #pragma unroll
-    for (int l = 0; l < Spline<S, LPT>::LEVELS; ++l) {
+    for (int l = 0; l < SP::LEVELS; ++l) {
         const int s = 1 << l;
         double Di[b][b];
         inv_small<b>(Dm, Di);
@@ -289,22 +315,20 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
             for (int c = 0; c < b; ++c) {
                 double dd = Dm[a][c], ln = 0.0, un = 0.0;
 #pragma unroll
-                for (int k = 0; k < b; ++k) {
-                    if (vm) { dd -= al[a][k] * Um[k][c]; ln -= al[a][k] * Lm[k][c]; }
-                    if (vp) { dd -= ga[a][k] * Lp[k][c]; un -= ga[a][k] * Up[k][c]; }
+                for (int k = 0; k < b; ++k) {   // al / ga are zero where the neighbour row does not exist
+                    dd = fma(-ga[a][k], Lp[k][c], fma(-al[a][k], Um[k][c], dd));
+                    ln = fma(-al[a][k], Lm[k][c], ln);
+                    un = fma(-ga[a][k], Up[k][c], un);
                 }
                 Dm[a][c] = dd; Ln[a][c] = ln; Un[a][c] = un;
-                sp.al[l][a][c] = al[a][c];
-                sp.ga[l][a][c] = ga[a][c];
+                sp.st.put(SP::ial(l, a, c), al[a][c]);
+                sp.st.put(SP::iga(l, a, c), ga[a][c]);
             }
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double acc = r[a][x];
 #pragma unroll
-                for (int k = 0; k < b; ++k) {
-                    if (vm) acc -= al[a][k] * rm[k][x];
-                    if (vp) acc -= ga[a][k] * rp[k][x];
-                }
+                for (int k = 0; k < b; ++k) acc = fma(-ga[a][k], rp[k][x], fma(-al[a][k], rm[k][x], acc));
                 r[a][x] = acc;
             }
         }
@@ -313,20 +337,26 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
 #pragma unroll
             for (int c = 0; c < b; ++c) { L[a][c] = Ln[a][c]; U[a][c] = Un[a][c]; }
     }
-    inv_small<b>(Dm, sp.Dinv);
+    double Dinv[b][b];
+    inv_small<b>(Dm, Dinv);
     double y[b][3];
 #pragma unroll
-    for (int a = 0; a < b; ++a)
+    for (int a = 0; a < b; ++a) {
+#pragma unroll
+        for (int k = 0; k < b; ++k) sp.st.put(SP::idi(a, k), Dinv[a][k]);
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < b; ++k) acc += sp.Dinv[a][k] * r[k][x];
+            for (int k = 0; k < b; ++k) acc += Dinv[a][k] * r[k][x];
             y[a][x] = acc;
         }
-    // boundary states of this piece, scaled: sh[d] = T^d * (d-th derivative)
+    }
+    // boundary states of this piece, scaled: sh[d] = T^d * (d-th derivative); rows 0..S-1 start,
+    // S..2S-1 end (row S holds dP = P1 - P0).  Not kept: spline_adjoint recomputes them from c.
+    double sh[D][3];
 #pragma unroll
-    for (int x = 0; x < 3; ++x) { sp.sh[0][x] = active ? P0[x] : 0.0; sp.sh[S][x] = dP[x]; }
+    for (int x = 0; x < 3; ++x) { sh[0][x] = active ? P0[x] : 0.0; sh[S][x] = dP[x]; }
 #pragma unroll
     for (int a = 0; a < b; ++a)
 #pragma unroll
@@ -334,8 +364,8 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
             const double yn = sh_dn<LPT>(mask, y[a][x], 1);
             const double ys = (lig == 0) ? hd[a][x] : y[a][x];
             const double ye = (lig == N - 1) ? td[a][x] : yn;
-            sp.sh[1 + a][x] = active ? lam[a + 1] * ys : 0.0;
-            sp.sh[S + 1 + a][x] = active ? lam[a + 1] * ye : 0.0;
+            sh[1 + a][x] = active ? lam[a + 1] * ys : 0.0;
+            sh[S + 1 + a][x] = active ? lam[a + 1] * ye : 0.0;
         }
     // Hermite -> monomial.  Hhat[k][0] == -Hhat[k][S] for k >= S: positions enter only through dP.
     double ip = 1.0;  // iT^k
@@ -345,11 +375,11 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
         for (int x = 0; x < 3; ++x) {
             double v;
             if (k < S) {
-                v = sp.sh[k][x] * (1.0 / cfact(k));
+                v = sh[k][x] * (1.0 / cfact(k));
             } else {
                 v = HK::H(k, S) * dP[x];
 #pragma unroll
-                for (int d = 1; d < S; ++d) v += HK::H(k, d) * sp.sh[d][x] + HK::H(k, S + d) * sp.sh[S + d][x];
+                for (int d = 1; d < S; ++d) v += HK::H(k, d) * sh[d][x] + HK::H(k, S + d) * sh[S + d][x];
             }
             chat[k][x] = v;
             sp.c[k][x] = v * ip;
@@ -360,8 +390,8 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
 
 // getEnergy + getEnergyPartialGradByCoeffs + getEnergyPartialGradByTimes for this piece
 // (SURVEY.md Appendix A.3 in normalised form: E_i = T^(1-2S) chat^T Qhat chat).
-template <int S, int LPT>
-__device__ __forceinline__ void energy_partials(const Spline<S, LPT> &sp, const double (&chat)[2 * S][3], bool active,
+template <int S, int LPT, class ST>
+__device__ __forceinline__ void energy_partials(const Spline<S, LPT, ST> &sp, const double (&chat)[2 * S][3], bool active,
                                                 double &energy, double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S;
     using HK = HermiteK<S>;
@@ -392,50 +422,79 @@ __device__ __forceinline__ void energy_partials(const Spline<S, LPT> &sp, const 
     gT = active ? sp.t5 * sp.iT * et : 0.0;
 }
 
-// 256-bit read-only load of one half-plane row (nx,ny,nz,d); rows are 32-byte aligned.
+// One half-plane row (nx,ny,nz,d); rows are 32-byte aligned.  PSMEM = true: the row sits in the
+// group's shared-memory stage (two LDS.128); false: 256-bit read-only global load.
 struct __align__(32) Plane { double x, y, z, w; };
+template <bool PSMEM>
 __device__ __forceinline__ Plane load_plane(const double *p) {
     Plane r;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    if (PSMEM) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(sa));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(r.z), "=d"(r.w) : "r"(sa));
+    } else {
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    }
     return r;
 }
 
 // attachPenaltyFunctional for this piece.  planes: this piece's rows.
-// Samples are processed in register blocks of JB so that each half-plane row is loaded once
-// per block instead of once per sample (L1 bandwidth, not DFMA, would bound the naive loop).
-template <int S, int LPT>
-__device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT> &sp, const double *planes,
-                                              int K, double &cost, double (&G)[2 * S][3], double &gT) {
+// Phase 1 tests a register block of JB sample positions against every half-plane, so each row is
+// loaded once per block instead of once per sample.  Phase 2 is a ROLLED loop over the samples of
+// the block (the position is recomputed, 15 DFMA, rather than indexed out of registers): the hot
+// loop has to stay inside the 32 KB instruction cache.
+template <int S, int LPT, bool PSMEM, class ST>
+__device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT, ST> &sp, const double *planes,
+                                              int rstride, int K, double &cost, double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S, JB = 6;
     const int kap = P.kappa;
     const double step = sp.T / kap;
     const double ikap = 1.0 / kap;
+    const double imu = 1.0 / P.mu;
+#pragma unroll 1
     for (int j0 = 0; j0 <= kap; j0 += JB) {
-        double pos[JB][3];
+        unsigned hit = 0u, pmask = 0u;
+        bool pwide = false;   // more than 32 rows: bit k&31 aliases, fall back to scanning every row
+        {
+            // sign-bit test: keep[jj] stays negative only while every n.p + d is negative; a sample
+            // with any value >= +0 is flagged and re-tested exactly (v > 0) in phase 2.
+            int keep[JB];
 #pragma unroll
-        for (int jj = 0; jj < JB; ++jj) {
-            const double s = (j0 + jj) * step;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double v = sp.c[D - 1][x];
-#pragma unroll
-                for (int k = D - 2; k >= 0; --k) v = fma(v, s, sp.c[k][x]);
-                pos[jj][x] = v;
-            }
-        }
-        unsigned hit = 0u;
-        for (int k = 0; k < K; ++k) {
-            const Plane h = load_plane(planes + 4 * k);
+            for (int jj = 0; jj < JB; ++jj) keep[jj] = -1;
+            pmask = 0u;
+            double pos[JB][3];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-                const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
-                hit |= (v > 0.0 ? 1u : 0u) << jj;
-            }
-        }
+                const double s = (j0 + jj) * step;
 #pragma unroll
-        for (int jj = 0; jj < JB; ++jj) {
+                for (int x = 0; x < 3; ++x) {
+                    double v = sp.c[D - 1][x];
+#pragma unroll
+                    for (int k = D - 2; k >= 0; --k) v = fma(v, s, sp.c[k][x]);
+                    pos[jj][x] = v;
+                }
+            }
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+#pragma unroll
+                int all = -1;
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
+                    keep[jj] &= __double2hiint(v);
+                    all &= __double2hiint(v);
+                }
+                pmask |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
+                pwide |= (k >= 32 && all >= 0);
+            }
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) hit |= (keep[jj] < 0 ? 0u : 1u) << jj;
+        }
+        const int jend = min(JB, kap + 1 - j0);
+#pragma unroll 1
+        for (int jj = 0; jj < jend; ++jj) {
             const int j = j0 + jj;
-            if (j <= kap) {
             const double s = j * step;
             // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
             double pw[D];
@@ -462,11 +521,27 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
                 double fv, df;
                 if (hp) {
+                    double pos[3];
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int k = D - 1; k >= 0; --k) v = fma(pw[k], sp.c[k][x], v);
+                        pos[x] = v;
+                    }
+                    // only rows flagged for this block (in row order, as the reference sums them)
+                    unsigned todo = pwide ? 0xffffffffu : pmask;
+#pragma unroll 1
                     for (int k = 0; k < K; ++k) {
-                        const Plane h = load_plane(planes + 4 * k);
-                        const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
+                        if (!pwide) {
+                            if (todo == 0u) break;
+                            k = __ffs(todo) - 1;
+                            todo &= todo - 1u;
+                        }
+                        const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+                        const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
                         if (v > 0.0) {
-                            smoothed_l1_pos(P.mu, v, fv, df);
+                            smoothed_l1_pos(P.mu, imu, v, fv, df);
                             const double wd = P.w_pos * df;
                             gP[0] += wd * h.x; gP[1] += wd * h.y; gP[2] += wd * h.z;
                             pena += P.w_pos * fv;
@@ -474,19 +549,19 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                     }
                 }
                 if (vv > 0.0) {
-                    smoothed_l1_pos(P.mu, vv, fv, df);
+                    smoothed_l1_pos(P.mu, imu, vv, fv, df);
                     const double wd = P.w_vel * df * 2.0;
                     gV[0] = wd * vel[0]; gV[1] = wd * vel[1]; gV[2] = wd * vel[2];
                     pena += P.w_vel * fv;
                 }
                 if (aa > 0.0) {
-                    smoothed_l1_pos(P.mu, aa, fv, df);
+                    smoothed_l1_pos(P.mu, imu, aa, fv, df);
                     const double wd = P.w_acc * df * 2.0;
                     gA[0] = wd * acc[0]; gA[1] = wd * acc[1]; gA[2] = wd * acc[2];
                     pena += P.w_acc * fv;
                 }
                 if (jj2 > 0.0) {
-                    smoothed_l1_pos(P.mu, jj2, fv, df);
+                    smoothed_l1_pos(P.mu, imu, jj2, fv, df);
                     const double wd = P.w_jerk * df * 2.0;
                     gJ[0] = wd * jer[0]; gJ[1] = wd * jer[1]; gJ[2] = wd * jer[2];
                     pena += P.w_jerk * fv;
@@ -513,15 +588,14 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 gT += dsum * (j * ikap) * w + node * pena * ikap;
                 cost += w * pena;
             }
-            }
         }
     }
 }
 
 // propogateGrad: G = dF/dc_i, gTp = partial dF/dT_i  ->  total dJ/dq_lig (junction lig, lanes
 // 1..N-1) and dJ/dT_lig (lanes 0..N-1).  See oracle/reduced_proto.py for the derivation.
-template <int S, int LPT>
-__device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, const Spline<S, LPT> &sp,
+template <int S, int LPT, class ST>
+__device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, const Spline<S, LPT, ST> &sp,
                                                const double (&G)[2 * S][3], double gTp, double (&gq)[3], double &gT) {
     constexpr int D = 2 * S, b = S - 1;
     using HK = HermiteK<S>;
@@ -553,6 +627,30 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
     lam[0] = 1.0;
 #pragma unroll
     for (int d = 1; d < S; ++d) lam[d] = lam[d - 1] * sp.T;
+    // scaled boundary states of this piece from its coefficients (chat_k = c_k T^k):
+    //   start sh[d] = d! chat_d,  end sh[S+d] = sum_k k!/(k-d)! chat_k,  sh[S] = dP = sum_{k>=1} chat_k
+    double sh[D][3];
+    {
+        double tk = 1.0;
+        double chat[D][3];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int x = 0; x < 3; ++x) chat[k][x] = active ? sp.c[k][x] * tk : 0.0;
+            tk *= sp.T;
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+#pragma unroll
+            for (int d = 0; d < S; ++d) {
+                sh[d][x] = cfact(d) * chat[d][x];
+                double e = 0.0;
+#pragma unroll
+                for (int k = D - 1; k >= (d == 0 ? 1 : d); --k) e += cfall(k, d) * chat[k][x];
+                sh[S + d][x] = e;
+            }
+        }
+    }
     // gather at junctions: g_y[j] = (L z)_{end, piece j-1} + (L z)_{start, piece j}
     double r[b][3], gp[3];
 #pragma unroll
@@ -567,7 +665,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
             const double ee = sh_up<LPT>(mask, active ? lam[a + 1] * z[S + 1 + a][x] : 0.0, 1);
             r[a][x] = junction ? ee + lam[a + 1] * z[1 + a][x] : 0.0;
         }
-    pcr_apply<S, LPT>(mask, lig, sp, r);  // r <- mu_lig
+    pcr_apply<S, LPT, ST>(mask, lig, sp, r);  // r <- mu_lig
     // m_i = [0, mu_i ; 0, mu_{i+1}], scaled by L
     double lm[D][3];
 #pragma unroll
@@ -588,11 +686,11 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
         double wm[D], ws[D];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            double vm = 0.0, vs = HK::W(a, S) * sp.sh[S][x];
+            double vm = 0.0, vs = HK::W(a, S) * sh[S][x];
 #pragma unroll
             for (int d = 1; d < S; ++d) {
                 vm += HK::W(a, d) * lm[d][x] + HK::W(a, S + d) * lm[S + d][x];
-                vs += HK::W(a, d) * sp.sh[d][x] + HK::W(a, S + d) * sp.sh[S + d][x];
+                vs += HK::W(a, d) * sh[d][x] + HK::W(a, S + d) * sh[S + d][x];
             }
             wm[a] = vm; ws[a] = vs;
         }
@@ -601,8 +699,8 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
         for (int d = 1; d < S; ++d) {
             acc_ms += lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d];
             acc_dms += (double)d * (lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d]);
-            acc_dsm += (double)d * (sp.sh[d][x] * wm[d] + sp.sh[S + d][x] * wm[S + d]);
-            zds += (double)d * (z[d][x] * sp.sh[d][x] + z[S + d][x] * sp.sh[S + d][x]);
+            acc_dsm += (double)d * (sh[d][x] * wm[d] + sh[S + d][x] * wm[S + d]);
+            zds += (double)d * (z[d][x] * sh[d][x] + z[S + d][x] * sh[S + d][x]);
         }
     }
     // dJ/dq_j = g_p[j] - t5_j wm_j[0] - (t5 wm[S])_{j-1}
@@ -617,20 +715,25 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
 }
 
 // ---- problem view ---------------------------------------------------------------------
+// What one group needs of its problem.  `planes` points at THIS LANE's first row and `rstride` is the
+// distance (in doubles) between consecutive rows of the lane's polytope:
+//   C-ABI layout in global memory  [N][K][4]:  planes = base + lig*K*4, rstride = 4
+//   shared-memory stage, plane-major [K][N][4]: planes = base + lig*4,   rstride = 4*N
+//     (for one k the lanes of a group read 32*N contiguous bytes: conflict-free LDS.128)
 struct ProblemView {
     const double *head;    // [S][3]
     const double *tail;    // [S][3]
-    const double *planes;  // [N][K][4] or nullptr
-    const int *hrows;      // [N] or nullptr
-    int K;
+    const double *planes;  // or nullptr
+    int rstride;
+    int rows;              // rows of this lane's polytope actually used (<= K)
 };
 
 // Whole cost functional for the group's trajectory.  xt = tau_lig, xq = q_lig (lanes 1..N-1).
 // Returns f on every lane of the group; gt = dJ/dtau_lig, gq = dJ/dq_lig.
-template <int S, int LPT>
+template <int S, int LPT, bool PSMEM, class ST>
 __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N,
-                                                  const ProblemView &pv, double xt, const double (&xq)[3],
-                                                  double &gt, double (&gq)[3]) {
+                                                  const ProblemView &pv, const ST &store, double xt,
+                                                  const double (&xq)[3], double &gt, double (&gq)[3]) {
     constexpr int D = 2 * S, b = S - 1;
     const bool active = lig < N;
     double P0[3], P1[3], hd[b][3], td[b][3];
@@ -648,17 +751,16 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
             td[a][x] = (lig == N - 1) ? pv.tail[(a + 1) * 3 + x] : 0.0;
         }
     const double T = active ? forward_t(xt) : 1.0;
-    Spline<S, LPT> sp;
+    Spline<S, LPT, ST> sp;
+    sp.st = store;
     double chat[D][3];
-    spline_solve<S, LPT>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
+    spline_solve<S, LPT, ST>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
     double cost, G[D][3], gTp;
-    energy_partials<S, LPT>(sp, chat, active, cost, G, gTp);
-    if (P.penalties && active) {
-        const int K = pv.hrows ? min(pv.hrows[lig], pv.K) : 0;
-        penalty_piece<S, LPT>(P, sp, pv.planes + (size_t)lig * pv.K * 4, pv.planes ? K : 0, cost, G, gTp);
-    }
+    energy_partials<S, LPT, ST>(sp, chat, active, cost, G, gTp);
+    if (P.penalties && active)
+        penalty_piece<S, LPT, PSMEM, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, cost, G, gTp);
     double gT;
-    spline_adjoint<S, LPT>(mask, lig, N, sp, G, gTp, gq, gT);
+    spline_adjoint<S, LPT, ST>(mask, lig, N, sp, G, gTp, gq, gT);
     if (active) cost += P.rho * T;
     gt = active ? backward_grad_t(xt, gT + P.rho) : 0.0;
     return group_sum<LPT>(mask, cost);

@@ -81,6 +81,7 @@ struct mincob_ctx {
     const double *head = nullptr, *tail = nullptr, *hpolys = nullptr;
     const int *hrows = nullptr;
     DevBuf b_head, b_tail, b_hpolys, b_hrows;          // set_problems (host) staging
+    DevBuf b_hist;                                     // L-BFGS (s, y) history slabs of the resident groups
     DevBuf b_x, b_f, b_g, b_status, b_iters, b_evals, b_coeffs, b_T, b_gather;  // host-pointer entry points
     DevBuf b_m0, b_m1, b_m2, b_m3, b_m4, b_m5, b_m6, b_m7, b_m8;      // minco_forward / propagate
     int *counter = nullptr;
@@ -171,7 +172,12 @@ static int launched(mincob_ctx *h, const LaunchResult &r, const char *what) {
 static int do_evaluate(mincob_ctx *h, const BatchArgs &a) {
     return launched(h, table_for(h->prm.S, a.N)->evaluate(h->stream, h->sm_count, h->dp, a), "evaluate_kernel");
 }
-static int do_optimize(mincob_ctx *h, const BatchArgs &a) {
+static int do_optimize(mincob_ctx *h, BatchArgs &a) {
+    const LaunchTable *t = table_for(h->prm.S, a.N);
+    const size_t need = t->optimize_scratch(h->sm_count, h->dp, a);
+    int rc = ensure(h, h->b_hist, need);
+    if (rc) return rc;
+    a.hist = (double *)h->b_hist.p;
     return launched(h, table_for(h->prm.S, a.N)->optimize(h->stream, h->sm_count, h->dp, a), "optimize_kernel");
 }
 static int do_minco(mincob_ctx *h, const MincoArgs &a, int propagate) {
@@ -284,7 +290,7 @@ int mincob_destroy(mincob_handle h) {
     if (!h) return MINCOB_E_INVALID;
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.destroy) g_nccl.destroy(h->comm);
-    DevBuf *bufs[] = {&h->b_head, &h->b_tail, &h->b_hpolys, &h->b_hrows, &h->b_x, &h->b_f, &h->b_g, &h->b_status,
+    DevBuf *bufs[] = {&h->b_head, &h->b_tail, &h->b_hpolys, &h->b_hist, &h->b_hrows, &h->b_x, &h->b_f, &h->b_g, &h->b_status,
                       &h->b_iters, &h->b_evals, &h->b_coeffs, &h->b_T, &h->b_gather, &h->b_m0, &h->b_m1, &h->b_m2, &h->b_m3,
                       &h->b_m4, &h->b_m5, &h->b_m6, &h->b_m7, &h->b_m8};
     for (DevBuf *b : bufs) release(*b);

@@ -264,6 +264,8 @@ def main():
     iters_mean = float(d_iters.to(torch.float64).mean().item())
     status = d_status.cpu().numpy()
     ok_frac = float((status >= 0).mean())
+    codes, cnts = np.unique(status, return_counts=True)
+    status_hist = {str(int(c)): int(k) for c, k in zip(codes, cnts)}
     evals_np = d_evals.cpu().numpy()
 
     # ---- e2e leg: host pointers through the C-ABI, copies inside the timed region -------------
@@ -339,7 +341,7 @@ def main():
                        "l2": "inputs larger than L2 (half-planes %.0f MB per GPU per step), no flush" % (pb.hpolys.nbytes / 1e6)},
             "evals_per_s": world * evals_sum * a.steps / (ms_tot * 1e-3),
             "mean_evals_per_traj": evals_sum / B, "p95_evals_per_traj": float(np.percentile(evals_np, 95)),
-            "mean_iters_per_traj": iters_mean, "ok_fraction": ok_frac,
+            "mean_iters_per_traj": iters_mean, "ok_fraction": ok_frac, "status_hist": status_hist,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": f"optimize_kernel<S={S}>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
