@@ -20,6 +20,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v
 INST = [(S, L) for S in (3, 4) for L in (8, 16, 32)]
 # resident blocks per SM the optimize kernel is compiled for (caps registers per thread); override for
 # experiments with MINCOB_MINB3 / MINCOB_MINB4 in the environment
+EXTRA = os.environ.get("MINCOB_EXTRA_FLAGS", "").split()
 MINB = {3: int(os.environ.get("MINCOB_MINB3", "2")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
 
 
@@ -58,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     for S, L in INST:
         o = os.path.join(OBJ, f"kernels_s{S}_l{L}.o")
-        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={MINB.get(S, 2)}", "-c",
+        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={MINB.get(S, 2)}", *EXTRA, "-c",
                       os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
     o = os.path.join(OBJ, "mincob.o")
     jobs.append(([nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))

@@ -15,6 +15,9 @@
 #pragma once
 #include "minco_device.cuh"
 
+#ifndef MINCOB_LOCKSTEP
+#define MINCOB_LOCKSTEP 0
+#endif
 #ifndef MINCOB_MINB
 #define MINCOB_MINB 2   // resident blocks per SM the optimize kernel is compiled for (register cap)
 #endif
@@ -189,7 +192,12 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             }
             __syncwarp();
         }
+#if MINCOB_LOCKSTEP
+        // the warps of a block walk the (cache-exceeding) evaluation code together, sharing its fetches
+        if (__syncthreads_and(phase == PH_IDLE)) break;
+#else
         if (__all_sync(FULL, phase == PH_IDLE)) break;
+#endif
 
         // ---- costFunctional --------------------------------------------------------------------
         double xq[3] = {x[1], x[2], x[3]}, gq[3];
@@ -206,10 +214,11 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
         // ---- per-group scalar decisions (no shuffles below until the next section) -------------
         int finish = 0, ret = 0;
         bool start_ls = false, upd = false, write_pf = false;
+        int pf_slot = 0;
         if (phase == PH_FIRST) {            // lbfgs.hpp:518-545
             evals = 1;
             fx = f;
-            write_pf = true;
+            write_pf = true;                // pf(0) = fx
             k = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] = -g[i];
@@ -258,13 +267,13 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 if (gn / fmax(1.0, xn) < P.g_eps) { ret = LBFGS_CONVERGENCE; finish = 1; }
                 if (!finish && past > 0) {
                     if (past <= k && fabs(pfk - fx) / fmax(1.0, fabs(fx)) < P.delta) { ret = LBFGS_STOP; finish = 1; }
-                    if (!finish) write_pf = true;
+                    if (!finish) { write_pf = true; pf_slot = k % past; }
                 }
                 if (!finish && P.max_iter != 0 && P.max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; finish = 1; }
                 if (!finish) upd = true;
             }
         }
-        if (write_pf && lig == 0) pf[past > 0 ? k % past : 0] = fx;
+        if (write_pf && lig == 0) pf[pf_slot] = fx;
 
         // ---- new iterate: (s, y) pair, cautious update, two-loop recursion (lbfgs.hpp:642-709) ----
         if (__any_sync(FULL, upd)) {
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 slot[1] = make_double4(yv[0], yv[1], yv[2], yv[3]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) d[i] = -g[i];
-                if (lig == 0) ysv[end] = ys;
+                if (lig == 0) ysv[end] = 1.0 / ys;   // the two-loop recursion only ever divides by y.s
                 two = ys > ss * sqrt(gpgp) * P.cautious;
                 if (two) {
                     ++bound;
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
                 const double4 s4 = slot[0], y4 = slot[1];
                 const double sj[4] = {s4.x, s4.y, s4.z, s4.w};
-                const double aj = gdot<LPT>(FULL, sj, d) / ysv[j];
+                const double aj = gdot<LPT>(FULL, sj, d) * ysv[j];
                 if (on) {
                     if (lig == 0) alpha[j] = aj;
                     d[0] -= aj * y4.x; d[1] -= aj * y4.y; d[2] -= aj * y4.z; d[3] -= aj * y4.w;
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
                 const double4 s4 = slot[0], y4 = slot[1];
                 const double yj[4] = {y4.x, y4.y, y4.z, y4.w};
-                const double beta = gdot<LPT>(FULL, yj, d) / ysv[j];
+                const double beta = gdot<LPT>(FULL, yj, d) * ysv[j];
                 if (on) {
                     const double cf = alpha[j] - beta;
                     d[0] += cf * s4.x; d[1] += cf * s4.y; d[2] += cf * s4.z; d[3] += cf * s4.w;

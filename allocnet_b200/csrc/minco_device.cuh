@@ -454,7 +454,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
 #pragma unroll 1
     for (int j0 = 0; j0 <= kap; j0 += JB) {
         unsigned hit = 0u, pmask = 0u;
-        bool pwide = false;   // more than 32 rows: bit k&31 aliases, fall back to scanning every row
+        const bool pwide = K > 32;   // more than 32 rows: bit k&31 aliases, scan every row instead
         {
             // sign-bit test: keep[jj] stays negative only while every n.p + d is negative; a sample
             // with any value >= +0 is flagged and re-tested exactly (v > 0) in phase 2.
@@ -486,7 +486,6 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                     all &= __double2hiint(v);
                 }
                 pmask |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
-                pwide |= (k >= 32 && all >= 0);
             }
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) hit |= (keep[jj] < 0 ? 0u : 1u) << jj;

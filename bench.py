@@ -180,7 +180,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from allocnet_b200 import api, synth
+    from allocnet_b200 import api, sharded, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,17 +197,14 @@ def main():
     B, N, K, S = a.batch, a.pieces, a.K, a.S
     n = 4 * N - 3
     # rank r owns problems [r*B, (r+1)*B) of the seeded stream (block partition)
-    pb = synth.make_problems(B, N=N, K=K, S=S, first=rank * B)
+    lo, hi = sharded.shard_range(world * B, world, rank)
+    pb = synth.make_problems(hi - lo, N=N, K=K, S=S, first=lo)
 
-    mb = api.MincoBatch(prm, device=local)
     # a real (non-legacy) stream shared by torch and the handle, so torch.cuda.Event brackets the launches
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    mb.set_stream(stream.cuda_stream)
-    if world > 1:
-        uid = [mb.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        mb.comm_init(world, rank, uid[0])
+    sh = sharded.ShardedMinco(prm, local, rank, world, dist if world > 1 else None, stream=stream.cuda_stream)
+    mb = sh.mb
 
     # ---- device-resident leg -------------------------------------------------------------
     t = lambda arr: torch.from_numpy(arr).to(dev)
@@ -230,9 +227,7 @@ def main():
 
     def step(record: bool):
         d_x.copy_(d_x0)                                   # fresh start point (x is in/out)
-        mb.optimize_device(d_x, d_f, d_status, d_iters, d_evals, d_coeffs, d_T)
-        if world > 1:
-            mb.allgather_device(d_coeffs, d_all, cnt)
+        sh.optimize_and_gather_device(d_x, d_f, d_status, d_iters, d_evals, d_coeffs, d_T, d_all, cnt)
         if record:
             kernel_ms.append(mb.last_kernel_ms()[0])      # CUDA events around the launch, on its stream
 

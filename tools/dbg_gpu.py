@@ -2,26 +2,17 @@ import sys, numpy as np
 sys.path.insert(0, '.')
 from allocnet_b200 import api, synth
 from allocnet_b200.params import default_params
-which = sys.argv[1]
-if which == "eval4":
-    prm = default_params(4); pb = synth.make_problems(8, N=8, K=16, S=4)
-    mb = api.MincoBatch(prm); mb.set_problems(pb); f, g = mb.evaluate(pb.x0()); print(f[:4])
-elif which == "opt3":
-    prm = default_params(3, max_iterations=int(sys.argv[2]) if len(sys.argv) > 2 else 1000); pb = synth.make_problems(8, N=8, K=16, S=3)
-    mb = api.MincoBatch(prm); mb.set_problems(pb); r = mb.optimize(pb.x0()); print(r["f"][:4], r["status"], r["evals"])
-elif which == "nearopt":
-    from oracle.pyoracle import Oracle
-    orc = Oracle()
-    prm = default_params(3); pb = synth.make_problems(512, N=8, K=16, S=3)
-    mb = api.MincoBatch(prm); mb.set_problems(pb); res = mb.optimize(pb.x0())
-    f, g = mb.evaluate(res["x"]); fo, go = orc.cost_batch(prm, pb, res["x"], nthreads=8)
-    ad = np.abs(g-go).max(axis=1); gn = np.abs(go).max(axis=1)
-    print("abs diff pct", np.percentile(ad,[50,90,99,100]))
-    print("gnorm pct", np.percentile(gn,[0,50,90,99,100]))
-    print("rel pct", np.percentile(ad/gn,[50,90,99,100]))
-    # oracle vs itself under perturbation of x by 1 ulp-ish (conditioning of the hinge gradient)
-    xp = res["x"]*(1+1e-15*np.sign(np.random.default_rng(0).normal(size=res["x"].shape)))
-    fo2, go2 = orc.cost_batch(prm, pb, xp, nthreads=8)
-    ad2 = np.abs(go2-go).max(axis=1)
-    print("oracle self-sensitivity to 1e-15 rel perturbation of x: abs diff pct", np.percentile(ad2,[50,90,99,100]))
-    print("status", np.unique(res["status"], return_counts=True), "evals mean", res["evals"].mean(), "iters", res["iters"].mean())
+z = np.load("tests/golden/s3_n16_k16.npz")
+pb = synth.make_problems(16, N=16, K=16, S=3)
+def show(tag, r):
+    print(tag, "f", np.round(r["f"][:5], 3), "st", r["status"][:5], "it", r["iters"][:5], "ev", r["evals"][:5])
+print("golden f", np.round(z["opt5000_f"][:5], 3), z["opt5000_iters"][:5])
+mb = api.MincoBatch(default_params(3, max_iterations=5000), device=0); mb.set_problems(pb)
+show("fresh 5000", mb.optimize(z["x0"]))
+mb.set_params(default_params(3, max_iterations=3)); show("cap 3", mb.optimize(z["x0"]))
+mb.set_params(default_params(3, max_iterations=5000)); show("after cap3, 5000", mb.optimize(z["x0"]))
+pb2 = synth.make_problems(128, N=16, K=16, S=3); mb.set_problems(pb2)
+show("B=128", mb.optimize(pb2.x0()))
+mb.set_problems(pb); show("B=16 again", mb.optimize(z["x0"]))
+for B in (1, 2, 8, 9, 16, 17):
+    pbb = synth.make_problems(B, N=16, K=16, S=3); mb.set_problems(pbb); show(f"B={B}", mb.optimize(pbb.x0()))
