@@ -21,7 +21,7 @@ INST = [(S, L) for S in (3, 4) for L in (8, 16, 32)]
 # resident blocks per SM the optimize kernel is compiled for (caps registers per thread); override for
 # experiments with MINCOB_MINB3 / MINCOB_MINB4 in the environment
 EXTRA = os.environ.get("MINCOB_EXTRA_FLAGS", "").split()
-MINB = {3: int(os.environ.get("MINCOB_MINB3", "2")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
+MINB = {3: int(os.environ.get("MINCOB_MINB3", "3")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
 
 
 def _nvcc():

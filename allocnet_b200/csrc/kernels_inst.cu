@@ -105,7 +105,7 @@ LaunchResult launch_evaluate(cudaStream_t st, int sm_count, const DevParams &dp,
 // shared memory when at least MINCOB_MINB blocks per SM still fit; otherwise they are read from global.
 struct OptPlan {
     int psmem, blocks;
-    size_t smem, hist_bytes, mult_bytes;
+    size_t smem, hist_bytes, mult_bytes, park_bytes;
     int code;
     cudaError_t err;
 };
@@ -119,17 +119,17 @@ static int blocks_per_sm(size_t smem, cudaError_t &e) {
     return e == cudaSuccess ? per_sm : 0;
 }
 static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs &a) {
-    OptPlan pl{0, 0, 0, 0, 0, 0, cudaSuccess};
+    OptPlan pl{0, 0, 0, 0, 0, 0, 0, cudaSuccess};
     const bool have = a.hpolys && a.hrows && a.K > 0;
     int per_sm = 0;
     if (have && dp.penalties) {
-        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 1) * sizeof(double);
+        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 1, LPT) * sizeof(double);
         per_sm = blocks_per_sm<true>(pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
         pl.psmem = per_sm >= MINCOB_MINB || per_sm >= 2;
     }
     if (!pl.psmem) {
-        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0) * sizeof(double);
+        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0, LPT) * sizeof(double);
         per_sm = blocks_per_sm<false>(pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
     }
@@ -140,13 +140,14 @@ static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs 
     pl.hist_bytes = (size_t)pl.blocks * GPB * dp.mem * LPT * 8 * sizeof(double);
     pl.hist_bytes = (pl.hist_bytes + 255) & ~(size_t)255;
     pl.mult_bytes = (size_t)pl.blocks * SplineReg<S, LPT>::NM * THREADS * sizeof(double);
+    pl.park_bytes = (size_t)pl.blocks * 12 * THREADS * sizeof(double);
     return pl;
 }
 
 // one allocation: [history slabs | multiplier slabs]
 size_t optimize_scratch(int sm_count, const DevParams &dp, const BatchArgs &a) {
     const OptPlan pl = plan_optimize(sm_count, dp, a);
-    return pl.hist_bytes + pl.mult_bytes;
+    return pl.hist_bytes + pl.mult_bytes + pl.park_bytes;
 }
 
 LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp, const BatchArgs &a) {
@@ -158,6 +159,7 @@ LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp,
     if ((e = cudaMemsetAsync(a.total_evals, 0, sizeof(unsigned long long), st)) != cudaSuccess) return ok(e);
     BatchArgs b = a;
     b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
+    b.lpark = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes + pl.mult_bytes);
     if (pl.psmem) optimize_kernel<S, LPT, THREADS, true><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
     else optimize_kernel<S, LPT, THREADS, false><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
     return ok(cudaGetLastError());

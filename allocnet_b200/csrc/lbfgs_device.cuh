@@ -15,6 +15,9 @@
 #pragma once
 #include "minco_device.cuh"
 
+#ifndef MINCOB_PARK
+#define MINCOB_PARK 1
+#endif
 #ifndef MINCOB_LOCKSTEP
 #define MINCOB_LOCKSTEP 0
 #endif
@@ -104,9 +107,9 @@ __device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, const Pro
 enum { PH_FETCH = 0, PH_FIRST = 1, PH_LS = 2, PH_IDLE = 3 };
 
 // doubles of shared memory one group needs (host and device must agree)
-__host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m, int past, int planes_in_smem) {
+__host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m, int past, int planes_in_smem, int lpt) {
     const int planes = planes_in_smem ? N * K * 4 : 0;
-    int small = 2 * S * 3 + 2 * m + (past > 0 ? past : 1);
+    int small = 2 * S * 3 + 2 * m + (past > 0 ? past : 1) + 12 + 4 * lpt;   // + parking: scalars (7 doubles, 8 ints), d
     small = (small + 3) & ~3;                      // keep every group's plane stage 32-byte aligned
     return planes + small;
 }
@@ -129,12 +132,15 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = P.mem, past = P.past;
 
     extern __shared__ __align__(32) double smem[];
-    double *grp = smem + (size_t)gib * optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0);
+    double *grp = smem + (size_t)gib * optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0, LPT);
     double *planes_s = grp;                                  // [K][N][4] when PSMEM
     double *ht = grp + (PSMEM ? N * K * 4 : 0);              // head [S][3], tail [S][3]
     double *alpha = ht + 2 * S * 3;
     double *ysv = alpha + m;
     double *pf = ysv + m;
+    double *park_d = pf + (past > 0 ? past : 1);             // L-BFGS scalars of the group while costFunctional runs
+    int *park_i = reinterpret_cast<int *>(park_d + 8);
+    double *park_dir = park_d + 12 + lig;                     // d of this lane (needed first after the evaluation): [4][LPT]
     // history slab of this group: [m][LPT][8] = (s0..s3, y0..y3) of lane lig in slot j
     double *hist = a.hist + ((size_t)blockIdx.x * (THREADS / LPT) + gib) * ((size_t)m * LPT * 8) + (size_t)lig * 8;
 
@@ -142,6 +148,9 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     GlobalStore mstore;
     mstore.p = a.mult + (size_t)blockIdx.x * SplineReg<S, LPT>::NM * THREADS + threadIdx.x;
     mstore.stride = THREADS;
+    GlobalStore lstore;   // xp, gp of this lane while the cost functional runs (8 of 12 slots used)
+    lstore.p = a.lpark + (size_t)blockIdx.x * 12 * THREADS + threadIdx.x;
+    lstore.stride = THREADS;
 
     int phase = PH_FETCH, prob = 0;
     ProblemView pv;
@@ -201,8 +210,40 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 
         // ---- costFunctional --------------------------------------------------------------------
         double xq[3] = {x[1], x[2], x[3]}, gq[3];
+#if MINCOB_PARK
+        // Nothing of the optimizer state is needed while the cost functional runs: park xp, gp, d in the
+        // lane-strided global slab and the group's scalars in shared memory, so that they do not hold
+        // ~60 registers across the penalty loop (which is what decides how many warps fit on an SM).
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { lstore.put(i, xp[i]); lstore.put(4 + i, gp[i]); park_dir[i * LPT] = d[i]; }
+            if (lig == 0) {
+                park_d[0] = fx; park_d[1] = stp; park_d[2] = finit; park_d[3] = dgtest; park_d[4] = dstest;
+                park_d[5] = lo; park_d[6] = hi;
+                park_i[0] = count; park_i[1] = k; park_i[2] = end; park_i[3] = bound; park_i[4] = evals;
+                park_i[5] = (bracketed ? 1 : 0) | (touched ? 2 : 0); park_i[6] = prob;
+            }
+            __syncwarp();
+        }
+#endif
+#if MINCOB_PARK
+        auto unpark = [&]() {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { xp[i] = lstore.get(i); gp[i] = lstore.get(4 + i); d[i] = park_dir[i * LPT]; }
+        };
+        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, pv, mstore, x[0], xq, g[0], gq, unpark);
+#else
         const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, pv, mstore, x[0], xq, g[0], gq);
+#endif
         g[1] = gq[0]; g[2] = gq[1]; g[3] = gq[2];
+#if MINCOB_PARK
+        {
+            fx = park_d[0]; stp = park_d[1]; finit = park_d[2]; dgtest = park_d[3]; dstest = park_d[4];
+            lo = park_d[5]; hi = park_d[6];
+            count = park_i[0]; k = park_i[1]; end = park_i[2]; bound = park_i[3]; evals = park_i[4];
+            bracketed = park_i[5] & 1; touched = (park_i[5] & 2) != 0; prob = park_i[6];
+        }
+#endif
 
         // ---- reductions every group may need ------------------------------------------------------
         const double gn = ginf<LPT>(FULL, g), xn = ginf<LPT>(FULL, x);
@@ -302,19 +343,37 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             }
             __syncwarp();
             const int nb = __reduce_max_sync(FULL, two ? bound : 0);
-            int j = end;
+            // The history sits in L2 (a 4 KB slab per trajectory, too big for what shared memory is left),
+            // every address of the recursion is known before it starts, and each step is a short dependent
+            // chain: keep two slots in flight ahead of the one being consumed.
+            // Backward pass, step i uses slot end-1-i (newest first); step 0 is the pair just computed.
+            struct Pair { double4 s, y; };
+            auto slot_at = [&](int i) {          // i-th newest slot of this group (i < m)
+                int jj = end - 1 - i;
+                return jj < 0 ? jj + m : jj;
+            };
+            auto fetch = [&](int jj) {
+                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)jj * LPT * 8);
+                Pair p;
+                p.s = slot[0]; p.y = slot[1];
+                return p;
+            };
+            Pair cur, n1;
+            cur.s = make_double4(sv[0], sv[1], sv[2], sv[3]);
+            cur.y = make_double4(yv[0], yv[1], yv[2], yv[3]);
+            n1 = fetch(slot_at(nb > 1 ? 1 : 0));
 #pragma unroll 1
             for (int i = 0; i < nb; ++i) {
                 const bool on = two && i < bound;
-                if (on) j = (j == 0 ? m : j) - 1;
-                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
-                const double4 s4 = slot[0], y4 = slot[1];
-                const double sj[4] = {s4.x, s4.y, s4.z, s4.w};
+                const Pair n2 = fetch(slot_at(i + 2 < nb ? i + 2 : nb - 1));
+                const int j = slot_at(i);
+                const double sj[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w};
                 const double aj = gdot<LPT>(FULL, sj, d) * ysv[j];
                 if (on) {
                     if (lig == 0) alpha[j] = aj;
-                    d[0] -= aj * y4.x; d[1] -= aj * y4.y; d[2] -= aj * y4.z; d[3] -= aj * y4.w;
+                    d[0] -= aj * cur.y.x; d[1] -= aj * cur.y.y; d[2] -= aj * cur.y.z; d[3] -= aj * cur.y.w;
                 }
+                cur = n1; n1 = n2;
             }
             __syncwarp();
             if (two) {
@@ -322,18 +381,22 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #pragma unroll
                 for (int u = 0; u < 4; ++u) d[u] *= sc0;
             }
+            // Forward pass, step i uses this group's (bound-1-i)-th newest slot (oldest first).
+            auto fwd_at = [&](int i) { return slot_at(bound - 1 - i > 0 ? bound - 1 - i : 0); };
+            cur = fetch(fwd_at(0));
+            n1 = fetch(fwd_at(1));
 #pragma unroll 1
             for (int i = 0; i < nb; ++i) {
                 const bool on = two && i < bound;
-                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)j * LPT * 8);
-                const double4 s4 = slot[0], y4 = slot[1];
-                const double yj[4] = {y4.x, y4.y, y4.z, y4.w};
+                const Pair n2 = fetch(fwd_at(i + 2));
+                const int j = fwd_at(i);
+                const double yj[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
                 const double beta = gdot<LPT>(FULL, yj, d) * ysv[j];
                 if (on) {
                     const double cf = alpha[j] - beta;
-                    d[0] += cf * s4.x; d[1] += cf * s4.y; d[2] += cf * s4.z; d[3] += cf * s4.w;
-                    j = (j + 1 == m) ? 0 : j + 1;
+                    d[0] += cf * cur.s.x; d[1] += cf * cur.s.y; d[2] += cf * cur.s.z; d[3] += cf * cur.s.w;
                 }
+                cur = n1; n1 = n2;
             }
         }
 

@@ -149,12 +149,10 @@ using SplineReg = Spline<S, LPT, RegStore<(2 * Log2<LPT>::value + 1) * (S - 1) *
 
 // PCR forward pass on the right-hand side only (uses the stored multipliers).
 template <int S, int LPT, class ST>
-__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const Spline<S, LPT, ST> &sp, double (&r)[S - 1][3]) {
+__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const double (&mul)[Spline<S, LPT, ST>::NM],
+                                          double (&r)[S - 1][3]) {
     constexpr int b = S - 1;
     using SP = Spline<S, LPT, ST>;
-    double mul[SP::NM];   // every multiplier of this lane, fetched up front (independent loads)
-#pragma unroll
-    for (int i = 0; i < SP::NM; ++i) mul[i] = sp.st.get(i);
 #pragma unroll
     for (int l = 0; l < SP::LEVELS; ++l) {
         const int s = 1 << l;
@@ -600,6 +598,11 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
     using HK = HermiteK<S>;
     const bool active = lig < N;
     const bool junction = (lig >= 1) && active;
+    // every PCR multiplier of this lane, requested first: with GlobalStore these are independent L2 loads
+    // whose latency the change of basis below covers
+    double mul[Spline<S, LPT, ST>::NM];
+#pragma unroll
+    for (int i = 0; i < Spline<S, LPT, ST>::NM; ++i) mul[i] = sp.st.get(i);
     // ghat_k = G_k / T^k ; z = Hhat^T ghat ; through-H time term  -(1/T) sum_k k G_k.c_k
     double gh[D][3];
     double ip = 1.0, kGc = 0.0;
@@ -664,7 +667,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
             const double ee = sh_up<LPT>(mask, active ? lam[a + 1] * z[S + 1 + a][x] : 0.0, 1);
             r[a][x] = junction ? ee + lam[a + 1] * z[1 + a][x] : 0.0;
         }
-    pcr_apply<S, LPT, ST>(mask, lig, sp, r);  // r <- mu_lig
+    pcr_apply<S, LPT, ST>(mask, lig, mul, r);  // r <- mu_lig
     // m_i = [0, mu_i ; 0, mu_{i+1}], scaled by L
     double lm[D][3];
 #pragma unroll
@@ -729,10 +732,15 @@ struct ProblemView {
 
 // Whole cost functional for the group's trajectory.  xt = tau_lig, xq = q_lig (lanes 1..N-1).
 // Returns f on every lane of the group; gt = dJ/dtau_lig, gq = dJ/dq_lig.
-template <int S, int LPT, bool PSMEM, class ST>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `before_adjoint` runs between the penalty loop and the adjoint: the optimize kernel uses it to request
+// its parked optimizer state early (plain loads whose latency the adjoint then covers).
+template <int S, int LPT, bool PSMEM, class ST, class Hook = NoHook>
 __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N,
                                                   const ProblemView &pv, const ST &store, double xt,
-                                                  const double (&xq)[3], double &gt, double (&gq)[3]) {
+                                                  const double (&xq)[3], double &gt, double (&gq)[3],
+                                                  Hook before_adjoint = Hook()) {
     constexpr int D = 2 * S, b = S - 1;
     const bool active = lig < N;
     double P0[3], P1[3], hd[b][3], td[b][3];
@@ -758,6 +766,7 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     energy_partials<S, LPT, ST>(sp, chat, active, cost, G, gTp);
     if (P.penalties && active)
         penalty_piece<S, LPT, PSMEM, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, cost, G, gTp);
+    before_adjoint();
     double gT;
     spline_adjoint<S, LPT, ST>(mask, lig, N, sp, G, gTp, gq, gT);
     if (active) cost += P.rho * T;
