@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int p
         const double T = active ? a.ts[(size_t)pp * N + lig] : 1.0;
         SplineReg<S, LPT> sp;
         double chat[D][3];
-        spline_solve<S, LPT>(mask, lig, Ne, T, P0, P1, hd, td, sp, chat);
+        spline_solve<S, LPT>(mask, lig, Ne, N > 2 ? N - 2 : 0, T, P0, P1, hd, td, sp, chat);
         if (!propagate) {
             double e, G[D][3], gT;
             energy_partials<S, LPT>(sp, chat, active, e, G, gT);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int p
                 for (int x = 0; x < 3; ++x)
                     G[k][x] = active ? a.gdC_in[((size_t)pp * D * N + (size_t)D * lig + k) * 3 + x] : 0.0;
             const double gTp = active ? a.gdT_in[(size_t)pp * N + lig] : 0.0;
-            spline_adjoint<S, LPT>(mask, lig, Ne, sp, G, gTp, gq, gT);
+            spline_adjoint<S, LPT>(mask, lig, Ne, N > 2 ? N - 2 : 0, sp, G, gTp, gq, gT);
             if (active) {
                 a.gradByTimes[(size_t)p * N + lig] = gT;
                 if (lig >= 1) {

@@ -69,7 +69,7 @@ __device__ __forceinline__ double ginf(unsigned m, const double (&a)[4]) {
 
 // setParameters + getTrajectory at x: writes Trajectory-order coefficients and durations.
 template <int S, int LPT>
-__device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, const ProblemView &pv,
+__device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, int rounds, const ProblemView &pv,
                                              const double (&xv)[4], double *coeffs, double *Tout) {
     constexpr int D = 2 * S, b = S - 1;
     constexpr unsigned mask = 0xffffffffu;  // called by whole warps only
@@ -91,7 +91,7 @@ __device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, const Pro
     const double T = active ? forward_t(xv[0]) : 1.0;
     SplineReg<S, LPT> sp;
     double chat[D][3];
-    spline_solve<S, LPT>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
+    spline_solve<S, LPT>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat);
     if (active) {
         if (coeffs) {
             // Trajectory<2S-1>: [piece][axis][k], k = 0 highest power (gcopter/trajectory.hpp:79-83)
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     const int lig = (threadIdx.x & 31) % LPT;
     const int gib = threadIdx.x / LPT;
     const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = P.mem, past = P.past;
+    const int rounds = N > 2 ? N - 2 : 0;   // lane-to-lane sweeps of the block solve (warp-uniform)
 
     extern __shared__ __align__(32) double smem[];
     double *grp = smem + (size_t)gib * optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0, LPT);
@@ -231,9 +232,9 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #pragma unroll
             for (int i = 0; i < 4; ++i) { xp[i] = lstore.get(i); gp[i] = lstore.get(4 + i); d[i] = park_dir[i * LPT]; }
         };
-        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, pv, mstore, x[0], xq, g[0], gq, unpark);
+        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, unpark);
 #else
-        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, pv, mstore, x[0], xq, g[0], gq);
+        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq);
 #endif
         g[1] = gq[0]; g[2] = gq[1]; g[3] = gq[2];
 #if MINCOB_PARK
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 }
             }
             if (a.coeffs || a.T)
-                emit_trajectory<S, LPT>(FULL, lig, finish ? N : 0, pv, x,
+                emit_trajectory<S, LPT>(FULL, lig, finish ? N : 0, rounds, pv, x,
                                         (finish && a.coeffs) ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
                                         (finish && a.T) ? a.T + (size_t)prob * N : nullptr);
             if (finish) phase = PH_FETCH;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(THREADS) evaluate_kernel(const DevParams P, co
         double xv[4], gt, gq[3];
         load_x<LPT>(a.x_in + (size_t)pp * n, live ? N : 0, lig, xv);
         double xq[3] = {xv[1], xv[2], xv[3]};
-        const double f = cost_functional<S, LPT, false>(P, 0xffffffffu, lig, live ? N : 0, pv, typename SplineReg<S, LPT>::ST_t(), xv[0], xq, gt, gq);
+        const double f = cost_functional<S, LPT, false>(P, 0xffffffffu, lig, live ? N : 0, N > 2 ? N - 2 : 0, pv, typename SplineReg<S, LPT>::ST_t(), xv[0], xq, gt, gq);
         if (live) {
             double gv[4] = {gt, gq[0], gq[1], gq[2]};
             store_x<LPT>(a.g_out + (size_t)p * n, N, lig, gv);

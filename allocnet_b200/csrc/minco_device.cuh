@@ -18,9 +18,11 @@
 //   E = sum_i s_i^T W(T_i) s_i,  W(T) = T^(1-2S) L What L,  L = diag(1,T,..,T^(S-1)) twice,
 // so y solves a symmetric positive definite BLOCK-TRIDIAGONAL system with (S-1)x(S-1) blocks
 // and one block row per junction.  Lane j builds block row j from T_{j-1}, T_j and the system is
-// solved by parallel cyclic reduction: log2(LPT) shuffle rounds instead of 2S*N pivots.  The
-// multipliers are kept so the adjoint solve (the matrix is symmetric) only touches right-hand
-// sides.  oracle/reduced_proto.py is the readable numpy statement of the same algebra and
+// solved by block elimination that sweeps from lane to lane with shuffles (N-2 short rounds of
+// (S-1)x(S-1) algebra instead of 2S*N scalar pivots); the sweep is a ROLLED loop, so the whole solve
+// is ~150 instructions of code -- what matters more than its latency, because the persistent
+// optimize kernel is instruction-cache bound (profiles/).  The multipliers are kept so the adjoint
+// solve (the matrix is symmetric) only touches right-hand sides.  oracle/reduced_proto.py is the readable numpy statement of the same algebra and
 // tests/test_reduced_formulation.py checks it against the banded oracle.
 // ============================================================================
 #pragma once
@@ -29,6 +31,10 @@
 
 #include "args.h"
 #include "hermite_constants.cuh"
+
+#ifndef MINCOB_UNROLL_JJ
+#define MINCOB_UNROLL_JJ 1   // samples per trip of the rolled phase-2 loop of penalty_piece
+#endif
 
 namespace mincob {
 
@@ -134,45 +140,49 @@ struct GlobalStore {
 // Per-lane (= per-piece) spline state kept between the forward solve and the adjoint.
 template <int S, int LPT, class ST>
 struct Spline {
-    static constexpr int D = 2 * S, b = S - 1, LEVELS = Log2<LPT>::value;
-    static constexpr int NM = (2 * LEVELS + 1) * b * b;   // al, ga per level + Dinv
+    static constexpr int D = 2 * S, b = S - 1;
+    static constexpr int NM = 3 * b * b;   // elimination multiplier M, inverse pivot block, upper block U
+    using ST_t = ST;
     double T, iT, t5;       // duration, 1/T, T^(1-2S)
     double c[D][3];         // monomial coefficients, ascending powers (row k = c_k)
-    using ST_t = ST;
-    ST st;                  // PCR multipliers of this block row
-    static __device__ __forceinline__ constexpr int ial(int l, int a, int k) { return ((2 * l) * b + a) * b + k; }
-    static __device__ __forceinline__ constexpr int iga(int l, int a, int k) { return ((2 * l + 1) * b + a) * b + k; }
-    static __device__ __forceinline__ constexpr int idi(int a, int k) { return (2 * LEVELS * b + a) * b + k; }
+    ST st;                  // factorisation of this lane's block row
+    static __device__ __forceinline__ constexpr int im(int a, int k) { return a * b + k; }
+    static __device__ __forceinline__ constexpr int idi(int a, int k) { return (b + a) * b + k; }
+    static __device__ __forceinline__ constexpr int iu(int a, int k) { return (2 * b + a) * b + k; }
 };
 template <int S, int LPT>
-using SplineReg = Spline<S, LPT, RegStore<(2 * Log2<LPT>::value + 1) * (S - 1) * (S - 1)>>;
+using SplineReg = Spline<S, LPT, RegStore<3 * (S - 1) * (S - 1)>>;
 
-// PCR forward pass on the right-hand side only (uses the stored multipliers).
+// Solve the factorised block-tridiagonal system for a new right-hand side r (in place).
+// Row j is  L_j y_{j-1} + D_j y_j + U_j y_{j+1} = r_j.  Forward: r'_j = r_j - M_j r'_{j-1}; backward:
+// y_j = Dinv_j (r'_j - U_j y_{j+1}).  Every lane recomputes its row from its own r and its neighbour's
+// current value each round, so after round t the rows up to t (from the far end: down to N-1-t) are
+// final and later rounds reproduce them: no lane-dependent predicate, `rounds` is warp-uniform.
 template <int S, int LPT, class ST>
-__device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const double (&mul)[Spline<S, LPT, ST>::NM],
-                                          double (&r)[S - 1][3]) {
+__device__ __forceinline__ void sweep_apply(unsigned mask, int rounds, const double (&fac)[Spline<S, LPT, ST>::NM],
+                                            double (&r)[S - 1][3]) {
     constexpr int b = S - 1;
     using SP = Spline<S, LPT, ST>;
+    double rr[b][3];
 #pragma unroll
-    for (int l = 0; l < SP::LEVELS; ++l) {
-        const int s = 1 << l;
-        double rm[b][3], rp[b][3];
+    for (int a = 0; a < b; ++a)
+#pragma unroll
+        for (int x = 0; x < 3; ++x) rr[a][x] = r[a][x];
+#pragma unroll 1
+    for (int t = 0; t < rounds; ++t) {
+        double rp[b][3];
 #pragma unroll
         for (int a = 0; a < b; ++a)
 #pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                rm[a][x] = sh_up<LPT>(mask, r[a][x], s);
-                rp[a][x] = sh_dn<LPT>(mask, r[a][x], s);
-            }
+            for (int x = 0; x < 3; ++x) rp[a][x] = sh_up<LPT>(mask, rr[a][x], 1);
 #pragma unroll
         for (int a = 0; a < b; ++a)
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double acc = r[a][x];
 #pragma unroll
-                for (int k = 0; k < b; ++k)   // al / ga are zero where the neighbour row does not exist
-                    acc = fma(-mul[SP::iga(l, a, k)], rp[k][x], fma(-mul[SP::ial(l, a, k)], rm[k][x], acc));
-                r[a][x] = acc;
+                for (int k = 0; k < b; ++k) acc = fma(-fac[SP::im(a, k)], rp[k][x], acc);
+                rr[a][x] = acc;
             }
     }
     double y[b][3];
@@ -182,9 +192,35 @@ __device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const double (
         for (int x = 0; x < 3; ++x) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < b; ++k) acc += mul[SP::idi(a, k)] * r[k][x];
+            for (int k = 0; k < b; ++k) acc = fma(fac[SP::idi(a, k)], rr[k][x], acc);
             y[a][x] = acc;
         }
+#pragma unroll 1
+    for (int t = 0; t < rounds; ++t) {
+        double yn[b][3], w[b][3];
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) yn[a][x] = sh_dn<LPT>(mask, y[a][x], 1);
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = rr[a][x];
+#pragma unroll
+                for (int k = 0; k < b; ++k) acc = fma(-fac[SP::iu(a, k)], yn[k][x], acc);
+                w[a][x] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < b; ++k) acc = fma(fac[SP::idi(a, k)], w[k][x], acc);
+                y[a][x] = acc;
+            }
+    }
 #pragma unroll
     for (int a = 0; a < b; ++a)
 #pragma unroll
@@ -194,8 +230,10 @@ __device__ __forceinline__ void pcr_apply(unsigned mask, int lig, const double (
 // setParameters: lane `lig` (< N active) holds piece lig with duration T, start position P0,
 // end position P1; hd/td are the head / tail derivatives 1..S-1 (used by lanes 0 / N-1).
 // Output: sp (coefficients + factorisation), chat (normalised coefficients c_k T^k).
+// `rounds` = (pieces of the launch) - 2, the same for every group of the warp (a group that is idle
+// passes N = 0 and carries identity rows through the same rounds).
 template <int S, int LPT, class ST>
-__device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, double Tin, const double (&P0)[3],
+__device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int rounds, double Tin, const double (&P0)[3],
                                              const double (&P1)[3], const double (&hd)[S - 1][3],
                                              const double (&td)[S - 1][3], Spline<S, LPT, ST> &sp,
                                              double (&chat)[2 * S][3]) {
@@ -267,88 +305,101 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, doub
             r[a][x] = junction ? -(ep + f[a][x]) : 0.0;
         }
     }
-    // parallel cyclic reduction
+    // forward elimination.  M_j = L_j Dinv'_{j-1};  D'_j = D_j - M_j U_{j-1} with U_{j-1} = L_j^T (symmetry);
+    // r'_j = r_j - M_j r'_{j-1}.  Each round every lane redoes its row from its ORIGINAL D, r and its
+    // neighbour's current values: row j is final after round j-1 and is reproduced unchanged afterwards.
+    double Dinv[b][b], M[b][b], rr[b][3];
+    inv_small<b>(Dm, Dinv);
 #pragma unroll
-    for (int l = 0; l < SP::LEVELS; ++l) {
-        const int s = 1 << l;
-        double Di[b][b];
-        inv_small<b>(Dm, Di);
-        const bool vm = lig >= s, vp = lig + s < LPT;
-        double al[b][b], ga[b][b], Um[b][b], Lm[b][b], Up[b][b], Lp[b][b], rm[b][3], rp[b][3];
-        {
-            double Dim[b][b], Dip[b][b];
+    for (int a = 0; a < b; ++a) {
 #pragma unroll
-            for (int a = 0; a < b; ++a)
+        for (int c = 0; c < b; ++c) M[a][c] = 0.0;
 #pragma unroll
-                for (int c = 0; c < b; ++c) {
-                    Dim[a][c] = sh_up<LPT>(mask, Di[a][c], s);
-                    Dip[a][c] = sh_dn<LPT>(mask, Di[a][c], s);
-                    Um[a][c] = sh_up<LPT>(mask, U[a][c], s);
-                    Lm[a][c] = sh_up<LPT>(mask, L[a][c], s);
-                    Up[a][c] = sh_dn<LPT>(mask, U[a][c], s);
-                    Lp[a][c] = sh_dn<LPT>(mask, L[a][c], s);
-                }
+        for (int x = 0; x < 3; ++x) rr[a][x] = r[a][x];
+    }
+#pragma unroll 1
+    for (int t = 0; t < rounds; ++t) {
+        double Dp[b][b], rp[b][3];
 #pragma unroll
-            for (int a = 0; a < b; ++a)
+        for (int a = 0; a < b; ++a) {
 #pragma unroll
-                for (int c = 0; c < b; ++c) {
-                    double sa = 0.0, sg = 0.0;
+            for (int c = 0; c < b; ++c) Dp[a][c] = sh_up<LPT>(mask, Dinv[a][c], 1);
 #pragma unroll
-                    for (int k = 0; k < b; ++k) { sa += L[a][k] * Dim[k][c]; sg += U[a][k] * Dip[k][c]; }
-                    al[a][c] = vm ? sa : 0.0;
-                    ga[a][c] = vp ? sg : 0.0;
-                }
+            for (int x = 0; x < 3; ++x) rp[a][x] = sh_up<LPT>(mask, rr[a][x], 1);
         }
-#pragma unroll
-        for (int a = 0; a < b; ++a)
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                rm[a][x] = sh_up<LPT>(mask, r[a][x], s);
-                rp[a][x] = sh_dn<LPT>(mask, r[a][x], s);
-            }
-        double Ln[b][b], Un[b][b];
+        double Dn[b][b];
 #pragma unroll
         for (int a = 0; a < b; ++a) {
 #pragma unroll
             for (int c = 0; c < b; ++c) {
-                double dd = Dm[a][c], ln = 0.0, un = 0.0;
+                double acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < b; ++k) {   // al / ga are zero where the neighbour row does not exist
-                    dd = fma(-ga[a][k], Lp[k][c], fma(-al[a][k], Um[k][c], dd));
-                    ln = fma(-al[a][k], Lm[k][c], ln);
-                    un = fma(-ga[a][k], Up[k][c], un);
-                }
-                Dm[a][c] = dd; Ln[a][c] = ln; Un[a][c] = un;
-                sp.st.put(SP::ial(l, a, c), al[a][c]);
-                sp.st.put(SP::iga(l, a, c), ga[a][c]);
+                for (int k = 0; k < b; ++k) acc = fma(L[a][k], Dp[k][c], acc);
+                M[a][c] = acc;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < b; ++a) {
+#pragma unroll
+            for (int c = 0; c < b; ++c) {
+                double acc = Dm[a][c];
+#pragma unroll
+                for (int k = 0; k < b; ++k) acc = fma(-M[a][k], L[c][k], acc);
+                Dn[a][c] = acc;
             }
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double acc = r[a][x];
 #pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(-ga[a][k], rp[k][x], fma(-al[a][k], rm[k][x], acc));
-                r[a][x] = acc;
+                for (int k = 0; k < b; ++k) acc = fma(-M[a][k], rp[k][x], acc);
+                rr[a][x] = acc;
             }
         }
-#pragma unroll
-        for (int a = 0; a < b; ++a)
-#pragma unroll
-            for (int c = 0; c < b; ++c) { L[a][c] = Ln[a][c]; U[a][c] = Un[a][c]; }
+        inv_small<b>(Dn, Dinv);
     }
-    double Dinv[b][b];
-    inv_small<b>(Dm, Dinv);
+    // back substitution  y_j = Dinv'_j (r'_j - U_j y_{j+1}), same scheme from the far end
     double y[b][3];
 #pragma unroll
     for (int a = 0; a < b; ++a) {
 #pragma unroll
-        for (int k = 0; k < b; ++k) sp.st.put(SP::idi(a, k), Dinv[a][k]);
+        for (int k = 0; k < b; ++k) {
+            sp.st.put(SP::im(a, k), M[a][k]);
+            sp.st.put(SP::idi(a, k), Dinv[a][k]);
+            sp.st.put(SP::iu(a, k), U[a][k]);
+        }
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < b; ++k) acc += Dinv[a][k] * r[k][x];
+            for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], rr[k][x], acc);
             y[a][x] = acc;
         }
+    }
+#pragma unroll 1
+    for (int t = 0; t < rounds; ++t) {
+        double yn[b][3], w[b][3];
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) yn[a][x] = sh_dn<LPT>(mask, y[a][x], 1);
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = rr[a][x];
+#pragma unroll
+                for (int k = 0; k < b; ++k) acc = fma(-U[a][k], yn[k][x], acc);
+                w[a][x] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], w[k][x], acc);
+                y[a][x] = acc;
+            }
     }
     // boundary states of this piece, scaled: sh[d] = T^d * (d-th derivative); rows 0..S-1 start,
     // S..2S-1 end (row S holds dP = P1 - P0).  Not kept: spline_adjoint recomputes them from c.
@@ -489,7 +540,8 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             for (int jj = 0; jj < JB; ++jj) hit |= (keep[jj] < 0 ? 0u : 1u) << jj;
         }
         const int jend = min(JB, kap + 1 - j0);
-#pragma unroll 1
+        constexpr int UJ = MINCOB_UNROLL_JJ;
+#pragma unroll UJ
         for (int jj = 0; jj < jend; ++jj) {
             const int j = j0 + jj;
             const double s = j * step;
@@ -592,13 +644,13 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
 // propogateGrad: G = dF/dc_i, gTp = partial dF/dT_i  ->  total dJ/dq_lig (junction lig, lanes
 // 1..N-1) and dJ/dT_lig (lanes 0..N-1).  See oracle/reduced_proto.py for the derivation.
 template <int S, int LPT, class ST>
-__device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, const Spline<S, LPT, ST> &sp,
+__device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, int rounds, const Spline<S, LPT, ST> &sp,
                                                const double (&G)[2 * S][3], double gTp, double (&gq)[3], double &gT) {
     constexpr int D = 2 * S, b = S - 1;
     using HK = HermiteK<S>;
     const bool active = lig < N;
     const bool junction = (lig >= 1) && active;
-    // every PCR multiplier of this lane, requested first: with GlobalStore these are independent L2 loads
+    // the factorisation of this lane's block row, requested first: with GlobalStore these are independent L2 loads
     // whose latency the change of basis below covers
     double mul[Spline<S, LPT, ST>::NM];
 #pragma unroll
@@ -667,7 +719,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, co
             const double ee = sh_up<LPT>(mask, active ? lam[a + 1] * z[S + 1 + a][x] : 0.0, 1);
             r[a][x] = junction ? ee + lam[a + 1] * z[1 + a][x] : 0.0;
         }
-    pcr_apply<S, LPT, ST>(mask, lig, mul, r);  // r <- mu_lig
+    sweep_apply<S, LPT, ST>(mask, rounds, mul, r);  // r <- mu_lig
     // m_i = [0, mu_i ; 0, mu_{i+1}], scaled by L
     double lm[D][3];
 #pragma unroll
@@ -737,7 +789,7 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // `before_adjoint` runs between the penalty loop and the adjoint: the optimize kernel uses it to request
 // its parked optimizer state early (plain loads whose latency the adjoint then covers).
 template <int S, int LPT, bool PSMEM, class ST, class Hook = NoHook>
-__device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N,
+__device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N, int rounds,
                                                   const ProblemView &pv, const ST &store, double xt,
                                                   const double (&xq)[3], double &gt, double (&gq)[3],
                                                   Hook before_adjoint = Hook()) {
@@ -761,14 +813,14 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     Spline<S, LPT, ST> sp;
     sp.st = store;
     double chat[D][3];
-    spline_solve<S, LPT, ST>(mask, lig, N, T, P0, P1, hd, td, sp, chat);
+    spline_solve<S, LPT, ST>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat);
     double cost, G[D][3], gTp;
     energy_partials<S, LPT, ST>(sp, chat, active, cost, G, gTp);
     if (P.penalties && active)
         penalty_piece<S, LPT, PSMEM, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, cost, G, gTp);
     before_adjoint();
     double gT;
-    spline_adjoint<S, LPT, ST>(mask, lig, N, sp, G, gTp, gq, gT);
+    spline_adjoint<S, LPT, ST>(mask, lig, N, rounds, sp, G, gTp, gq, gT);
     if (active) cost += P.rho * T;
     gt = active ? backward_grad_t(xt, gT + P.rho) : 0.0;
     return group_sum<LPT>(mask, cost);
