@@ -282,3 +282,38 @@ def test_round_trip_properties_full_size(handles):
     assert ok2.mean() >= 0.995
     assert (res2["f"][ok2] <= res["f"][ok2] * (1 + 1e-12)).all()
     assert np.median(res2["iters"]) <= 10
+
+
+def test_gpu_trajectory_in_reference_class(handles, oracle):
+    """What the device writes as `coeffs`/`T` goes into the REFERENCE's Trajectory<5> (gcopter/trajectory.hpp
+    compiled verbatim, oracle/_ref) through emplace_back, as learning_planner.hpp:205-216 does: the
+    reference's getPositions must return head, the optimized waypoints and tail, and twice its
+    getTrajCost(3) must be the jerk energy the device reports for the same (q, T)."""
+    import ctypes as C
+    ref = oracle.ref
+    if ref is None or not hasattr(ref, "ref_traj5_create"):
+        pytest.skip("oracle/_ref not present")
+    dp = C.POINTER(C.c_double)
+    ref.ref_traj5_create.restype = C.c_void_p; ref.ref_traj5_create.argtypes = [C.c_int, dp, dp]
+    ref.ref_traj5_destroy.argtypes = [C.c_void_p]
+    ref.ref_traj5_cost.restype = C.c_double; ref.ref_traj5_cost.argtypes = [C.c_void_p, C.c_int]
+    ref.ref_traj5_positions.argtypes = [C.c_void_p, dp]
+    B, N = 64, 8
+    pb = synth.make_problems(B, N=N, K=16, S=3)
+    mb = handles[3]
+    mb.set_params(default_params(3))
+    mb.set_problems(pb)
+    res = mb.optimize(pb.x0())
+    q = res["x"][:, N:].reshape(B, N - 1, 3)
+    fw = mb.minco_forward(pb.head, pb.tail, q, res["T"])
+    for b in range(B):
+        c = np.ascontiguousarray(res["coeffs"][b]); T = np.ascontiguousarray(res["T"][b])
+        h = ref.ref_traj5_create(N, T.ctypes.data_as(dp), c.ctypes.data_as(dp))
+        try:
+            P = np.zeros((N + 1, 3)); ref.ref_traj5_positions(h, P.ctypes.data_as(dp))
+            np.testing.assert_allclose(P[0], pb.head[b, 0], atol=1e-9)
+            np.testing.assert_allclose(P[1:N], q[b], atol=1e-8)
+            np.testing.assert_allclose(P[N], pb.tail[b, 0], atol=1e-7)
+            assert abs(2.0 * ref.ref_traj5_cost(h, 3) - fw["energy"][b]) <= 1e-9 * abs(fw["energy"][b])
+        finally:
+            ref.ref_traj5_destroy(h)

@@ -269,3 +269,75 @@ def test_mpmath_certifies_fp64_oracle(oracle):
             c[:, a] = [float(col[i]) for i in range(D * N)]
         out = oracle.minco_forward(S, head, tail, q, T)
         assert np.max(np.abs(out["coeffs"] - c)) <= 1e-10 * max(1.0, np.abs(c).max())
+
+
+def test_smoothed_l1_equals_reference_function(oracle_strict):
+    """firi.hpp:60-84 itself (cut out of the reference file by oracle/Makefile and compiled unmodified into
+    oracle/_ref) against the oracle's restatement: bit-equal on a grid that covers x<0, the quartic blend and
+    the linear branch, for several mu."""
+    import ctypes as C
+    ref = oracle_strict.ref
+    if ref is None or not hasattr(ref, "ref_smoothed_l1"):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ref.ref_smoothed_l1.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(5)
+    for mu in (1e-2, 1e-3, 0.5):
+        xs = np.concatenate([np.linspace(-2 * mu, 3 * mu, 401), rng.uniform(-mu, 2 * mu, 500), [0.0, mu, np.nextafter(mu, 1)]])
+        for x in xs:
+            f, df = C.c_double(-7.0), C.c_double(-7.0)
+            hit = ref.ref_smoothed_l1(mu, float(x), C.byref(f), C.byref(df))
+            h2, f2, df2 = oracle_strict.smoothed_l1(mu, float(x))
+            assert bool(hit) == h2
+            if hit:
+                assert f.value == f2 and df.value == df2, (mu, x)
+
+
+def test_output_contract_against_reference_trajectory(oracle):
+    """The reference's own Piece<5>/Trajectory<5> (gcopter/trajectory.hpp, compiled verbatim into oracle/_ref)
+    fed with getTrajectory-order coefficients exactly as learning_planner.hpp:205-216 feeds it:
+    getPos/getVel/getAcc/getJer reproduce the spline (descending powers, trajectory.hpp:79-133),
+    getPositions returns head, waypoints, tail, locatePieceIdx walks the durations, and the reference's
+    energy formula gives E_MINCO == 2 * getTrajCost(3) (trajectory.hpp:396-420)."""
+    import ctypes as C
+    ref = oracle.ref
+    if ref is None or not hasattr(ref, "ref_traj5_create"):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    dp = C.POINTER(C.c_double)
+    ref.ref_traj5_create.restype = C.c_void_p
+    ref.ref_traj5_create.argtypes = [C.c_int, dp, dp]
+    ref.ref_traj5_destroy.argtypes = [C.c_void_p]
+    ref.ref_traj5_cost.restype = C.c_double; ref.ref_traj5_cost.argtypes = [C.c_void_p, C.c_int]
+    ref.ref_traj5_total_duration.restype = C.c_double; ref.ref_traj5_total_duration.argtypes = [C.c_void_p]
+    ref.ref_traj5_eval.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, dp]
+    ref.ref_traj5_positions.argtypes = [C.c_void_p, dp]
+    ref.ref_traj5_locate.argtypes = [C.c_void_p, dp]
+    rng = np.random.default_rng(11)
+    for N in (1, 2, 5, 8):
+        head = rng.normal(size=(3, 3)); tail = rng.normal(size=(3, 3))
+        q = np.cumsum(rng.normal(size=(max(N - 1, 1), 3)), axis=0)[: N - 1]
+        T = rng.uniform(0.5, 2.5, size=N)
+        out = oracle.minco_forward(3, head, tail, q, T)
+        flat = np.ascontiguousarray(out["flat"]); Tc = np.ascontiguousarray(T)
+        h = ref.ref_traj5_create(N, Tc.ctypes.data_as(dp), flat.ctypes.data_as(dp))
+        try:
+            assert abs(2.0 * ref.ref_traj5_cost(h, 3) - out["energy"]) <= 1e-12 * abs(out["energy"])
+            assert abs(ref.ref_traj5_total_duration(h) - T.sum()) <= 1e-14 * T.sum()
+            P = np.zeros((N + 1, 3)); ref.ref_traj5_positions(h, P.ctypes.data_as(dp))
+            np.testing.assert_allclose(P[0], head[0], atol=1e-12)
+            np.testing.assert_allclose(P[1:N], q, atol=1e-9)
+            np.testing.assert_allclose(P[N], tail[0], atol=1e-9)
+            c = out["coeffs"].reshape(N, 6, 3)                     # ascending powers, row k = c_k
+            t0 = np.concatenate([[0.0], np.cumsum(T)])
+            for t in rng.uniform(0.0, T.sum(), size=12):
+                tl = C.c_double(t); i = ref.ref_traj5_locate(h, C.byref(tl))
+                assert i == min(np.searchsorted(t0, t, side="left") - 1, N - 1) or t == 0.0
+                s_ = t - t0[i]
+                assert abs(tl.value - s_) <= 1e-12
+                got = [np.zeros(3) for _ in range(4)]
+                ref.ref_traj5_eval(h, t, *[g.ctypes.data_as(dp) for g in got])
+                for d, g in enumerate(got):
+                    fac = np.array([np.prod([k - u for u in range(d)]) if k >= d else 0.0 for k in range(6)])
+                    want = (c[i] * (fac * s_ ** np.maximum(np.arange(6) - d, 0))[:, None]).sum(axis=0)
+                    np.testing.assert_allclose(g, want, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(want).max()))
+        finally:
+            ref.ref_traj5_destroy(h)
