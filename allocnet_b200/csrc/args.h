@@ -32,6 +32,7 @@ enum {
 struct DevParams {
     int kappa;
     double mu, w_pos, w_vel, w_acc, w_jerk, vmax2, amax2, jmax2, rho;
+    double imu, ikap;   // 1/mu, 1/kappa (an fp64 division is ~30 instructions on the device)
     int penalties;  // 0: energy-only fast path (all weights zero)
     // L-BFGS (gcopter/lbfgs.hpp:15-129)
     int mem, past, max_iter, max_ls;

@@ -497,9 +497,8 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                                               int rstride, int K, double &cost, double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S, JB = 6;
     const int kap = P.kappa;
-    const double step = sp.T / kap;
-    const double ikap = 1.0 / kap;
-    const double imu = 1.0 / P.mu;
+    const double ikap = P.ikap, imu = P.imu;
+    const double step = sp.T * ikap;
 #pragma unroll 1
     for (int j0 = 0; j0 <= kap; j0 += JB) {
         unsigned hit = 0u, pmask = 0u;

@@ -130,6 +130,7 @@ static int derive(mincob_ctx *h) {
     if (!(p.mu > 0.0)) return fail(h, MINCOB_E_INVALID, "mu must be > 0");
     DevParams &d = h->dp;
     d.kappa = p.kappa; d.mu = p.mu;
+    d.imu = 1.0 / p.mu; d.ikap = 1.0 / p.kappa;
     d.w_pos = p.w_pos; d.w_vel = p.w_vel; d.w_acc = p.w_acc; d.w_jerk = p.w_jerk;
     d.vmax2 = p.v_max * p.v_max; d.amax2 = p.a_max * p.a_max; d.jmax2 = p.j_max * p.j_max;
     d.rho = p.rho;
