@@ -75,6 +75,8 @@ CASES = [  # (S, N, K, B, ragged, energy_only)
     (3, 2, 7, 33, False, False),
     (3, 12, 9, 65, True, False),
     (3, 32, 16, 40, False, False),    # MINCOB_MAX_PIECES
+    (3, 8, 40, 96, True, False),      # > 32 rows per polytope: no row bitmask, half-planes read from global memory
+    (3, 5, 50, 64, True, False),      # the reference pads polytopes to 50 rows, ModelMaxSeg = 5 (learning_planner.hpp:157-168)
     (4, 8, 16, 512, False, False),    # MINCO_S4NU
     (4, 5, 16, 64, True, False),
 ]
@@ -149,7 +151,8 @@ def test_optimize_trace_matches_oracle(handles, oracle):
     handles[3].set_params(default_params(3))
 
 
-@pytest.mark.parametrize("S,N,K,B", [(3, 8, 16, 1024), (3, 5, 16, 200), (3, 16, 16, 128), (4, 8, 16, 128), (3, 8, 0, 256)])
+@pytest.mark.parametrize("S,N,K,B", [(3, 8, 16, 1024), (3, 5, 16, 200), (3, 16, 16, 128), (4, 8, 16, 128), (3, 8, 0, 256),
+                                     (3, 5, 50, 96), (3, 32, 8, 24)])
 def test_optimize_converges_like_oracle(handles, oracle, S, N, K, B):
     """Full runs: every problem ends with a success code on both sides; the device's reported cost
     at its final x equals the oracle's cost at that x (1e-9); its coefficients equal the oracle's
