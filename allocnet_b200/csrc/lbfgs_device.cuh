@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     // history slab of this group: [m][LPT][8] = (s0..s3, y0..y3) of lane lig in slot j
     double *hist = a.hist + ((size_t)blockIdx.x * (THREADS / LPT) + gib) * ((size_t)m * LPT * 8) + (size_t)lig * 8;
 
-    // PCR multipliers of the current evaluation: slot i of thread t at mult[(block*NM + i)*THREADS + t]
+    // block-solve multipliers of the current evaluation: slot i of thread t at mult[(block*NM + i)*THREADS + t]
     GlobalStore mstore;
     mstore.p = a.mult + (size_t)blockIdx.x * SplineReg<S, LPT>::NM * THREADS + threadIdx.x;
     mstore.stride = THREADS;

@@ -39,11 +39,6 @@
 namespace mincob {
 
 
-template <int V>
-struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
-template <>
-struct Log2<1> { static constexpr int value = 0; };
-
 // d! and k!/(k-d)!: loop form (no recursion) so that they fold to literals once the surrounding
 // loops are unrolled, and stay cheap straight-line code if they are not.
 __host__ __device__ __forceinline__ constexpr double cfact(int d) {
@@ -57,11 +52,6 @@ __host__ __device__ __forceinline__ constexpr double cfall(int k, int d) {
     return f;
 }
 
-template <int LPT>
-__device__ __forceinline__ unsigned group_mask() {
-    if (LPT == 32) return 0xffffffffu;
-    return ((1u << (LPT & 31)) - 1u) << (((threadIdx.x & 31) / LPT) * LPT);
-}
 template <int LPT> __device__ __forceinline__ double sh_up(unsigned m, double v, int d) { return __shfl_up_sync(m, v, d, LPT); }
 template <int LPT> __device__ __forceinline__ double sh_dn(unsigned m, double v, int d) { return __shfl_down_sync(m, v, d, LPT); }
 template <int LPT> __device__ __forceinline__ double sh_xor(unsigned m, double v, int d) { return __shfl_xor_sync(m, v, d, LPT); }
@@ -120,7 +110,7 @@ __device__ __forceinline__ void inv_small<3>(const double (&d)[3][3], double (&o
     o[2][2] = (d[0][0] * d[1][1] - d[0][1] * d[1][0]) * r;
 }
 
-// Where a lane keeps its PCR multipliers between setParameters and propogateGrad: NM doubles that
+// Where a lane keeps its block-solve multipliers between setParameters and propogateGrad: NM doubles that
 // are written once and read once per evaluation.  RegStore holds them in registers (short kernels);
 // GlobalStore parks them in a lane-strided global slab (coalesced, L2-resident) so that they do not
 // occupy 2*NM registers across the penalty loop of the persistent optimize kernel.

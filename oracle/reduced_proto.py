@@ -16,7 +16,10 @@ s_i = [start derivs 0..S-1 ; end derivs 0..S-1] (Hermite form, c_i = H(T_i) s_i)
 
 and dE/dy_j = 0 is a symmetric positive definite BLOCK-TRIDIAGONAL system with (S-1)x(S-1) blocks
 and N-1 block rows: 7 block rows of 2x2 for N=8, S=3.  One lane per piece builds its own blocks
-from T_i and the system is solved by parallel cyclic reduction (log2 steps, warp shuffles).
+from T_i and the system is solved by the lane-to-lane block elimination sweep the kernels use
+(`sweep_solve`: N-2 rounds in which EVERY row recomputes itself from its own data and its neighbour's
+current value, so the loop body has no row-dependent predicate); the first kernel versions used
+parallel cyclic reduction (`pcr_solve`, kept as a cross-check).
 
 Adjoint.  With G_i = dF/dc_i (energy + penalties) and the partial dF/dT_i, let
 z_i = Hhat^T Gamma G_i (Gamma = diag(T^-k)), g_s = L z_i, gather g_y at junctions, solve
@@ -122,6 +125,50 @@ def pcr_resolve(fact, R):
     return np.einsum("nab,nbm->nam", Dinv, R)
 
 
+def sweep_solve(Lb, Db, Ub, R, rounds=None):
+    """Block elimination as the device does it (allocnet_b200/csrc/minco_device.cuh: spline_solve).
+
+    Forward:  M_j = L_j Dinv'_{j-1},  D'_j = D_j - M_j U_{j-1},  r'_j = r_j - M_j r'_{j-1};
+    backward: y_j = Dinv'_j (r'_j - U_j y_{j+1}).
+    Every round ALL rows are recomputed from their ORIGINAL D, r and the neighbour's current values (a
+    Jacobi sweep): row j is final after round j and is reproduced unchanged afterwards, so n-1 rounds
+    are exact for n rows and any larger warp-uniform count is harmless."""
+    n, b = Db.shape[0], Db.shape[1]
+    rounds = max(n - 1, 0) if rounds is None else rounds
+    Lb = Lb.copy(); Ub = Ub.copy()
+    Lb[0] = 0.0; Ub[n - 1] = 0.0
+    Dinv = np.linalg.inv(Db)
+    rr = R.copy()
+    M = np.zeros_like(Db)
+    for _ in range(rounds):
+        Dp = np.concatenate([np.eye(b)[None], Dinv[:-1]])          # shuffle-up by one row
+        Up = np.concatenate([np.zeros((1, b, b)), Ub[:-1]])
+        rp = np.concatenate([np.zeros_like(R[:1]), rr[:-1]])
+        M = np.einsum("nab,nbc->nac", Lb, Dp)
+        Dn = Db - np.einsum("nab,nbc->nac", M, Up)
+        rr = R - np.einsum("nab,nbm->nam", M, rp)
+        Dinv = np.linalg.inv(Dn)
+    y = np.einsum("nab,nbm->nam", Dinv, rr)
+    for _ in range(rounds):
+        yn = np.concatenate([y[1:], np.zeros_like(y[:1])])          # shuffle-down by one row
+        y = np.einsum("nab,nbm->nam", Dinv, rr - np.einsum("nab,nbm->nam", Ub, yn))
+    return y, (M, Dinv, Ub, rounds)
+
+
+def sweep_resolve(fact, R):
+    """Same factorisation, new right-hand side (allocnet_b200/csrc/minco_device.cuh: sweep_apply)."""
+    M, Dinv, Ub, rounds = fact
+    rr = R.copy()
+    for _ in range(rounds):
+        rp = np.concatenate([np.zeros_like(R[:1]), rr[:-1]])
+        rr = R - np.einsum("nab,nbm->nam", M, rp)
+    y = np.einsum("nab,nbm->nam", Dinv, rr)
+    for _ in range(rounds):
+        yn = np.concatenate([y[1:], np.zeros_like(y[:1])])
+        y = np.einsum("nab,nbm->nam", Dinv, rr - np.einsum("nab,nbm->nam", Ub, yn))
+    return y
+
+
 class ReducedMinco:
     """Same call sequence as orc::Minco<S> (setConditions/setParameters/.../propogateGrad)."""
 
@@ -178,7 +225,7 @@ class ReducedMinco:
                 if j == N - 1:
                     r -= Wn[np.ix_(ia, ib)] @ Y[N]
                 R[j - 1] = r
-            X, self.fact = pcr_solve(Lb, Db, Ub, R)
+            X, self.fact = sweep_solve(Lb, Db, Ub, R)
             Y[1:N] = X
         self.P, self.Y, self.Wl = P, Y, Wl
         # boundary states and coefficients
@@ -212,7 +259,7 @@ class ReducedMinco:
             gp[j - 1] = gs[j - 1, S] + gs[j, 0]
         MU = np.zeros((N + 1, b, 3))
         if N > 1:
-            MU[1:N] = pcr_resolve(self.fact, gy)
+            MU[1:N] = sweep_resolve(self.fact, gy)
         gq = gp.copy(); gT = np.zeros(N)
         for i in range(N):
             m = np.zeros((D, 3))

@@ -1,10 +1,10 @@
-"""The junction-state (block-tridiagonal + cyclic reduction) formulation used by the CUDA kernels,
+"""The junction-state (block-tridiagonal + lane-to-lane elimination sweep) formulation used by the CUDA kernels,
 stated in numpy (oracle/reduced_proto.py), must reproduce the banded MINCO oracle: coefficients
 (setParameters) and propogateGrad, for S = 3 and 4 and every piece count the kernels accept."""
 import numpy as np
 import pytest
 
-from oracle.reduced_proto import ReducedMinco, hermite_constants, pcr_solve, pcr_resolve
+from oracle.reduced_proto import ReducedMinco, hermite_constants, pcr_solve, pcr_resolve, sweep_solve, sweep_resolve
 
 
 def _rand(rng, S, N):
@@ -70,3 +70,9 @@ def test_pcr_matches_dense():
         R2 = rng.normal(size=(n, b, 3))
         np.testing.assert_allclose(pcr_resolve(fact, R2).reshape(n * b, 3), np.linalg.solve(M, R2.reshape(n * b, 3)),
                                    rtol=0, atol=1e-12)
+        # the sweep the kernels use now; extra (warp-uniform) rounds must not change the answer
+        for extra in (0, 3):
+            X, fact = sweep_solve(Lb, Db, Ub, R, rounds=max(n - 1, 0) + extra)
+            np.testing.assert_allclose(X.reshape(n * b, 3), np.linalg.solve(M, R.reshape(n * b, 3)), rtol=0, atol=1e-12)
+            np.testing.assert_allclose(sweep_resolve(fact, R2).reshape(n * b, 3), np.linalg.solve(M, R2.reshape(n * b, 3)),
+                                       rtol=0, atol=1e-12)
