@@ -1,0 +1,21 @@
+#!/bin/bash
+# smoke(), compute-sanitizer (memcheck + racecheck) on a small optimize/evaluate, full GPU tests
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+cat > /tmp/san.py <<'PY'
+import numpy as np, sys
+sys.path.insert(0, '.')
+from allocnet_b200 import api, synth
+from allocnet_b200.params import default_params
+for S, N, K, B in ((3, 8, 16, 96), (3, 5, 50, 40), (4, 8, 16, 40), (3, 16, 16, 24), (3, 1, 4, 8)):
+    prm = default_params(S, max_iterations=12)
+    pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=(K == 50))
+    mb = api.MincoBatch(prm, device=0); mb.set_problems(pb)
+    f, g = mb.evaluate(pb.x0()); r = mb.optimize(pb.x0())
+    q = pb.q0; out = mb.minco_forward(pb.head, pb.tail, q, pb.T0)
+    print(S, N, K, B, float(f[0]), int(r["evals"].sum()))
+    mb.close()
+PY
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python /tmp/san.py > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
