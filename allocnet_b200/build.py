@@ -62,7 +62,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={MINB.get(S, 2)}", *EXTRA, "-c",
                       os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
     o = os.path.join(OBJ, "mincob.o")
-    jobs.append(([nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))
+    jobs.append(([nvcc, *ARCH, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         outs = list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
     if verbose:

@@ -156,7 +156,11 @@ LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp,
     if (pl.code) return LaunchResult{cudaSuccess, pl.code, pl.smem};
     cudaError_t e;
     if ((e = cudaMemsetAsync(a.counter, 0, sizeof(int), st)) != cudaSuccess) return ok(e);
-    if ((e = cudaMemsetAsync(a.total_evals, 0, sizeof(unsigned long long), st)) != cudaSuccess) return ok(e);
+    if ((e = cudaMemsetAsync(a.total_evals, 0, 128 * sizeof(unsigned long long), st)) != cudaSuccess) return ok(e);
+#ifdef MINCOB_TIMING
+    cudaMemsetAsync(a.total_evals + 1, 0xff, sizeof(unsigned long long), st);
+    cudaMemsetAsync(a.total_evals + 3, 0xff, sizeof(unsigned long long), st);
+#endif
     BatchArgs b = a;
     b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
     b.lpark = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes + pl.mult_bytes);

@@ -153,6 +153,12 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     lstore.p = a.lpark + (size_t)blockIdx.x * 12 * THREADS + threadIdx.x;
     lstore.stride = THREADS;
 
+#ifdef MINCOB_TIMING
+    if (threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMin(a.total_evals + 3, t);
+    }
+#endif
     int phase = PH_FETCH, prob = 0;
     ProblemView pv;
     pv.head = ht; pv.tail = ht + S * 3; pv.planes = nullptr; pv.rstride = 4; pv.rows = 0;
@@ -171,6 +177,15 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             p = __shfl_sync(FULL, p, 0, LPT);
             if (want) {
                 if (p >= a.B) {
+#ifdef MINCOB_TIMING
+                    if (lig == 0) {   // experiment: when did the work queue run dry / how many groups idle over time
+                        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                        atomicMin(a.total_evals + 1, t);
+                        const unsigned long long t0 = *(volatile unsigned long long *)(a.total_evals + 1);
+                        const unsigned long long bin = (t - t0) / 1000000ull;   // 1 ms bins after the queue ran dry
+                        if (bin < 64) atomicAdd(a.total_evals + 4 + bin, 1ull);
+                    }
+#endif
                     phase = PH_IDLE; prob = 0;
                     for (int i = lig; i < 2 * S * 3; i += LPT) ht[i] = 0.0;
                     pv.planes = nullptr; pv.rows = 0;
@@ -446,6 +461,12 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
         }
     }
     if (a.total_evals && my_evals) atomicAdd(a.total_evals, my_evals);
+#ifdef MINCOB_TIMING
+    if (threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMax(a.total_evals + 2, t);
+    }
+#endif
 }
 
 // One launch = the lbfgs_evaluate_t callback body for every problem of the batch.

@@ -279,7 +279,7 @@ int mincob_create(mincob_handle *out, const mincob_params *params, int device) {
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     if (cudaMalloc((void **)&h->counter, sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void **)&h->total_evals, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc((void **)&h->total_evals, 128 * sizeof(unsigned long long)) != cudaSuccess) {
         mincob_destroy(h);
         return MINCOB_E_ALLOC;
     }
@@ -601,6 +601,17 @@ int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *stat
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
+
+#ifdef MINCOB_TIMING
+// experiment builds only (tools/): [0] evaluations, [1] time the queue ran dry, [2] kernel end, [3] kernel start (ns),
+// [4..67] groups going idle per millisecond after [1]
+extern "C" int mincob_debug_counters(mincob_handle h, unsigned long long *out, int n) {
+    if (!h || !out || n > 128) return MINCOB_E_INVALID;
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(out, h->total_evals, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+#endif
 
 int mincob_host_alloc(void **out, uint64_t bytes) {
     if (!out) return MINCOB_E_INVALID;
