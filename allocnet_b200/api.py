@@ -32,6 +32,7 @@ SYMBOLS = [
     "mincob_optimize", "mincob_optimize_device", "mincob_last_kernel_ms", "mincob_minco_forward",
     "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
+    "mincob_check_feasibility", "mincob_check_feasibility_device",
 ]
 
 
@@ -76,6 +77,8 @@ def load_library() -> C.CDLL:
     L.mincob_optimize_sharded.argtypes = [_vp] + [_vp] * 7
     L.mincob_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
     L.mincob_host_free.argtypes = [_vp]
+    L.mincob_check_feasibility.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
+    L.mincob_check_feasibility_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     _lib = L
     return L
 
@@ -222,6 +225,17 @@ class MincoBatch:
         self._check(self.L.mincob_minco_propagate(self.h, B, N, _np_ptr(head), _np_ptr(tail), _np_ptr(inPs), _np_ptr(ts),
                                                   _np_ptr(gdC), _np_ptr(gdT), _np_ptr(gq), _np_ptr(gT)))
         return gq[:, : N - 1], gT
+
+    # -- feasibility report (sampled Piece::getMaxVelRate / getMaxAccRate / corridor residual) ------
+    def check_feasibility(self, coeffs, T, samples: int = 64):
+        """-> [B][4]: max |v|, max |a|, max |j|, max_k(n_k.p + d_k) over samples+1 points per piece."""
+        coeffs, T = _f64(coeffs), _f64(T)
+        rep = np.zeros((self.B, 4))
+        self._check(self.L.mincob_check_feasibility(self.h, _np_ptr(coeffs), _np_ptr(T), int(samples), _np_ptr(rep)))
+        return rep
+
+    def check_feasibility_device(self, coeffs, T, samples, report):
+        self._check(self.L.mincob_check_feasibility_device(self.h, _dev_ptr(coeffs), _dev_ptr(T), int(samples), _dev_ptr(report)))
 
     # -- multi-GPU ---------------------------------------------------------------------------
     def nccl_unique_id(self) -> bytes:

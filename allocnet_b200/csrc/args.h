@@ -67,4 +67,14 @@ struct MincoArgs {
     double *gradByPoints, *gradByTimes;        // propagate
 };
 
+// sampled feasibility report of optimized trajectories (the job of Piece::getMaxVelRate / checkMaxAccRate,
+// gcopter/trajectory.hpp:177-314, on a fixed grid instead of by root finding)
+struct CheckArgs {
+    int B, N, K, samples;          // `samples` sub-intervals per piece (samples + 1 points, both ends)
+    const double *coeffs, *T;      // [B][N][3][2S] Trajectory order, [B][N]
+    const double *hpolys;          // [B][N][K][4] or nullptr
+    const int *hrows;
+    double *out;                   // [B][4]: max |v|, max |a|, max |j|, max_k (n_k.p + d_k)  (<= 0: inside the corridor)
+};
+
 }  // namespace mincob

@@ -85,6 +85,59 @@ __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int p
     }
 }
 
+// ---- feasibility report: one lane per piece, `samples`+1 points per piece, group-wide max ---------------
+template <int S, int LPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) check_kernel(const CheckArgs a) {
+    constexpr int D = 2 * S;
+    const int lig = (threadIdx.x & 31) % LPT;
+    const unsigned mask = 0xffffffffu;
+    const int N = a.N;
+    const int groups = gridDim.x * (THREADS / LPT);
+    const int rounds = (a.B + groups - 1) / groups;
+    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    for (int it = 0; it < rounds; ++it, p += groups) {
+        const bool live = p < a.B && lig < N;
+        double vmax = 0.0, amax = 0.0, jmax = 0.0, cmax = -1.0e300;
+        if (live) {
+            const double *c = a.coeffs + ((size_t)p * N + lig) * 3 * D;   // [3][2S], k = 0 highest power
+            const double T = a.T[(size_t)p * N + lig];
+            const bool planes = a.hpolys && a.hrows && a.K > 0;
+            const double *hp = planes ? a.hpolys + ((size_t)p * N + lig) * a.K * 4 : nullptr;
+            const int rows = planes ? min(a.hrows[(size_t)p * N + lig], a.K) : 0;
+            for (int j = 0; j <= a.samples; ++j) {
+                const double t = T * j / a.samples;
+                double pos[3], v2 = 0.0, a2 = 0.0, j2 = 0.0;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    // Horner on the value and its first three derivatives (scaled by 1/d!) together;
+                    // descending coefficients as in Piece<D>, trajectory.hpp:75-133
+                    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        q3 = fma(q3, t, q2);
+                        q2 = fma(q2, t, q1);
+                        q1 = fma(q1, t, q0);
+                        q0 = fma(q0, t, c[x * D + k]);
+                    }
+                    q2 *= 2.0; q3 *= 6.0;
+                    pos[x] = q0; v2 += q1 * q1; a2 += q2 * q2; j2 += q3 * q3;
+                }
+                vmax = fmax(vmax, v2); amax = fmax(amax, a2); jmax = fmax(jmax, j2);
+                for (int k = 0; k < rows; ++k) {
+                    const Plane h = load_plane<false>(hp + 4 * k);
+                    cmax = fmax(cmax, fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w))));
+                }
+            }
+        }
+        vmax = group_max<LPT>(mask, vmax); amax = group_max<LPT>(mask, amax);
+        jmax = group_max<LPT>(mask, jmax); cmax = group_max<LPT>(mask, cmax);
+        if (p < a.B && lig == 0) {
+            double *o = a.out + (size_t)p * 4;
+            o[0] = sqrt(vmax); o[1] = sqrt(amax); o[2] = sqrt(jmax); o[3] = cmax;
+        }
+    }
+}
+
 }  // namespace mincob
 
 namespace {
@@ -177,7 +230,15 @@ LaunchResult launch_minco(cudaStream_t st, int sm_count, const MincoArgs &a, int
     return ok(cudaGetLastError());
 }
 
-const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco, optimize_scratch};
+LaunchResult launch_check(cudaStream_t st, int sm_count, const CheckArgs &a) {
+    int blocks = (a.B + GPB - 1) / GPB;
+    const int cap = sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    check_kernel<S, LPT, THREADS><<<blocks, THREADS, 0, st>>>(a);
+    return ok(cudaGetLastError());
+}
+
+const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco, optimize_scratch, launch_check};
 }  // namespace
 
 #define MINCOB_CAT_(a, b, c) mincob_table_##a##_##b

@@ -16,6 +16,7 @@ struct LaunchTable {
     LaunchResult (*minco)(cudaStream_t, int sm_count, const MincoArgs &, int propagate);
     // bytes of global scratch (L-BFGS history slabs) `optimize` needs in BatchArgs::hist
     size_t (*optimize_scratch)(int sm_count, const DevParams &, const BatchArgs &);
+    LaunchResult (*check)(cudaStream_t, int sm_count, const CheckArgs &);
 };
 }  // namespace mincob
 const mincob::LaunchTable *mincob_table_3_8();

@@ -540,6 +540,35 @@ int mincob_minco_propagate(mincob_handle h, int B, int N, const double *head, co
     return 0;
 }
 
+// ---- feasibility report --------------------------------------------------------------------
+int mincob_check_feasibility_device(mincob_handle h, const double *coeffs, const double *T, int samples, double *report) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!coeffs || !T || !report || samples < 1) return fail(h, MINCOB_E_INVALID, "coeffs, T, report must be non-null and samples >= 1");
+    CU(h, cudaSetDevice(h->device));
+    CheckArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = h->B; a.N = h->N; a.K = h->K; a.samples = samples;
+    a.coeffs = coeffs; a.T = T; a.hpolys = h->hpolys; a.hrows = h->hrows; a.out = report;
+    return launched(h, table_for(h->prm.S, a.N)->check(h->stream, h->sm_count, a), "check_kernel");
+}
+
+int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double *T, int samples, double *report) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!coeffs || !T || !report) return fail(h, MINCOB_E_INVALID, "coeffs, T, report must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const size_t B = h->B, N = h->N, S = h->prm.S;
+    const size_t nc = B * N * 3 * 2 * S * 8, nt = B * N * 8, nr = B * 4 * 8;
+    if ((rc = up(h, h->b_coeffs, coeffs, nc)) || (rc = up(h, h->b_T, T, nt)) || (rc = ensure(h, h->b_m0, nr))) return rc;
+    if ((rc = mincob_check_feasibility_device(h, (const double *)h->b_coeffs.p, (const double *)h->b_T.p, samples,
+                                              (double *)h->b_m0.p)))
+        return rc;
+    if ((rc = down(h, report, h->b_m0, nr))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------
 int mincob_nccl_unique_id(void *uid) {
     if (!uid) return MINCOB_E_INVALID;

@@ -263,6 +263,18 @@ def main():
     status_hist = {str(int(c)): int(k) for c, k in zip(codes, cnts)}
     evals_np = d_evals.cpu().numpy()
 
+    # ---- quality of what was produced (outside the timed region): sampled limits and corridor residual ----
+    d_rep = torch.empty(B, 4, dtype=torch.float64, device=dev)
+    mb.check_feasibility_device(d_coeffs, d_T, 32, d_rep)
+    torch.cuda.synchronize(dev)
+    rep = d_rep.cpu().numpy()
+    quality = {"samples_per_piece": 33,
+               "v_within_2pct": float((rep[:, 0] <= 1.02 * float(prm.v_max)).mean()),
+               "a_within_2pct": float((rep[:, 1] <= 1.02 * float(prm.a_max)).mean()),
+               "j_within_2pct": float((rep[:, 2] <= 1.02 * float(prm.j_max)).mean()),
+               "corridor_within_2cm": float((rep[:, 3] <= 0.02).mean()) if K > 0 else None,
+               "max_speed_p99": float(np.percentile(rep[:, 0], 99))}
+
     # ---- e2e leg: host pointers through the C-ABI, copies inside the timed region -------------
     e2e = None
     if not a.no_e2e:
@@ -336,7 +348,7 @@ def main():
                        "l2": "inputs larger than L2 (half-planes %.0f MB per GPU per step), no flush" % (pb.hpolys.nbytes / 1e6)},
             "evals_per_s": world * evals_sum * a.steps / (ms_tot * 1e-3),
             "mean_evals_per_traj": evals_sum / B, "p95_evals_per_traj": float(np.percentile(evals_np, 95)),
-            "mean_iters_per_traj": iters_mean, "ok_fraction": ok_frac, "status_hist": status_hist,
+            "mean_iters_per_traj": iters_mean, "ok_fraction": ok_frac, "status_hist": status_hist, "quality": quality,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": f"optimize_kernel<S={S}>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,

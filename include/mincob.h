@@ -126,6 +126,16 @@ int mincob_minco_propagate(mincob_handle h, int B, int N, const double *head, co
                            const double *inPs, const double *ts, const double *gdC, const double *gdT,
                            double *gradByPoints, double *gradByTimes);
 
+/* ---- feasibility report of optimized trajectories: what Piece::getMaxVelRate / getMaxAccRate /
+ *      checkMaxVelRate (gcopter/trajectory.hpp:177-314) answer by root finding, on a fixed grid of
+ *      `samples`+1 points per piece (both ends included), plus the largest corridor residual against
+ *      the polytopes of the current mincob_set_problems call.
+ *      coeffs [B][N][3][2S] and T [B][N] as returned by mincob_optimize;
+ *      report [B][4] = max |v|, max |a|, max |j|, max_k (n_k.p + d_k)   (last entry <= 0: inside). */
+int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double *T, int samples, double *report);
+int mincob_check_feasibility_device(mincob_handle h, const double *coeffs_d, const double *T_d, int samples,
+                                    double *report_d);
+
 /* ---- multi-GPU: one process per GPU, problems block-partitioned, ONE all-gather of the solved
  *      coefficients (BASELINE.json north_star).  unique_id is the 128-byte ncclUniqueId made
  *      on rank 0 by mincob_nccl_unique_id and broadcast by the caller (torch.distributed). */

@@ -320,3 +320,55 @@ def test_gpu_trajectory_in_reference_class(handles, oracle):
             assert abs(2.0 * ref.ref_traj5_cost(h, 3) - fw["energy"][b]) <= 1e-9 * abs(fw["energy"][b])
         finally:
             ref.ref_traj5_destroy(h)
+
+
+def test_feasibility_report(handles, oracle):
+    """mincob_check_feasibility (sampled max |v|, |a|, |j| and corridor residual) against numpy on the same
+    grid, and -- for the derivative values themselves -- against the reference's Trajectory<5>::getVel/getAcc/
+    getJer (gcopter/trajectory.hpp compiled verbatim, oracle/_ref) at the same times."""
+    import ctypes as C
+    B, N, K, R = 48, 8, 16, 24
+    pb = synth.make_problems(B, N=N, K=K, S=3)
+    mb = handles[3]
+    mb.set_params(default_params(3))
+    mb.set_problems(pb)
+    res = mb.optimize(pb.x0())
+    rep = mb.check_feasibility(res["coeffs"], res["T"], samples=R)
+    c = res["coeffs"]; T = res["T"]                       # [B][N][3][6] descending
+    pw = np.arange(5, -1, -1)
+    u = np.linspace(0.0, 1.0, R + 1)
+    want = np.zeros((B, 4)); want[:, 3] = -np.inf
+    for i in range(N):
+        t = T[:, i, None] * np.arange(R + 1)[None, :] / R  # same expression as the kernel: T*j/R
+        def deriv(d):
+            fac = np.array([np.prod([k - q for q in range(d)]) if k >= d else 0.0 for k in pw])
+            tp = np.where(pw[None, None, :] >= d, t[:, :, None] ** np.maximum(pw - d, 0)[None, None, :], 0.0)
+            return np.einsum("bak,btk->bta", c[:, i] * fac[None, None, :], tp)
+        for col, d in ((0, 1), (1, 2), (2, 3)):
+            want[:, col] = np.maximum(want[:, col], np.linalg.norm(deriv(d), axis=2).max(axis=1))
+        pos = deriv(0)
+        hp = pb.hpolys[:, i]                              # [B][K][4]
+        viol = np.einsum("bkx,btx->btk", hp[:, :, :3], pos) + hp[:, None, :, 3]
+        want[:, 3] = np.maximum(want[:, 3], viol.reshape(B, -1).max(axis=1))
+    np.testing.assert_allclose(rep[:, :3], want[:, :3], rtol=1e-9)
+    np.testing.assert_allclose(rep[:, 3], want[:, 3], rtol=1e-9, atol=1e-9)
+    # the optimizer did its job: limits (4, 6, 12) and corridor hold up to the softness of the penalty
+    assert np.median(rep[:, 0]) <= 4.0 * 1.02 and np.median(rep[:, 1]) <= 6.0 * 1.02 and np.median(rep[:, 3]) <= 0.02
+    ref = oracle.ref
+    if ref is not None and hasattr(ref, "ref_traj5_create"):
+        dp = C.POINTER(C.c_double)
+        ref.ref_traj5_create.restype = C.c_void_p; ref.ref_traj5_create.argtypes = [C.c_int, dp, dp]
+        ref.ref_traj5_destroy.argtypes = [C.c_void_p]
+        ref.ref_traj5_eval.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, dp]
+        for b in range(0, B, 7):
+            cc = np.ascontiguousarray(c[b]); TT = np.ascontiguousarray(T[b])
+            h = ref.ref_traj5_create(N, TT.ctypes.data_as(dp), cc.ctypes.data_as(dp))
+            vm = 0.0
+            t0 = np.concatenate([[0.0], np.cumsum(TT)])
+            for i in range(N):
+                for j in range(1, R):                     # interior points: no piece-boundary ambiguity
+                    o = [np.zeros(3) for _ in range(4)]
+                    ref.ref_traj5_eval(h, t0[i] + TT[i] * j / R, *[q.ctypes.data_as(dp) for q in o])
+                    vm = max(vm, np.linalg.norm(o[1]))
+            ref.ref_traj5_destroy(h)
+            assert vm <= rep[b, 0] * (1 + 1e-9) and vm >= rep[b, 0] * 0.97
