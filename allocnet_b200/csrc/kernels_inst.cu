@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(THREADS) check_kernel(const CheckArgs a) {
 
 namespace {
 using namespace mincob;
-constexpr int S = MINCOB_S, LPT = MINCOB_LPT, THREADS = 128, GPB = THREADS / LPT;
+#ifndef MINCOB_THREADS
+#define MINCOB_THREADS 128   // threads per block of every kernel here (experiments: 256 / 384 with MINCOB_LOCKSTEP)
+#endif
+constexpr int S = MINCOB_S, LPT = MINCOB_LPT, THREADS = MINCOB_THREADS, GPB = THREADS / LPT;
 
 LaunchResult ok(cudaError_t e) { return LaunchResult{e, 0, 0}; }
 
@@ -162,9 +165,11 @@ struct OptPlan {
     int code;
     cudaError_t err;
 };
-template <bool PSMEM>
+// history depth the register-resident two-loop recursion is compiled for (upstream default of this build, params.py)
+constexpr int FASTMEM = 8;
+template <bool PSMEM, int MEM>
 static int blocks_per_sm(size_t smem, cudaError_t &e) {
-    auto kern = optimize_kernel<S, LPT, THREADS, PSMEM>;
+    auto kern = optimize_kernel<S, LPT, THREADS, PSMEM, MEM>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { e = cudaSuccess; (void)cudaGetLastError(); return 0; }
     int per_sm = 0;
@@ -177,13 +182,13 @@ static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs 
     int per_sm = 0;
     if (have && dp.penalties) {
         pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 1, LPT) * sizeof(double);
-        per_sm = blocks_per_sm<true>(pl.smem, pl.err);
+        per_sm = dp.mem == FASTMEM ? blocks_per_sm<true, FASTMEM>(pl.smem, pl.err) : blocks_per_sm<true, 0>(pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
         pl.psmem = per_sm >= MINCOB_MINB || per_sm >= 2;
     }
     if (!pl.psmem) {
         pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0, LPT) * sizeof(double);
-        per_sm = blocks_per_sm<false>(pl.smem, pl.err);
+        per_sm = dp.mem == FASTMEM ? blocks_per_sm<false, FASTMEM>(pl.smem, pl.err) : blocks_per_sm<false, 0>(pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
     }
     if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
@@ -217,8 +222,13 @@ LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp,
     BatchArgs b = a;
     b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
     b.lpark = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes + pl.mult_bytes);
-    if (pl.psmem) optimize_kernel<S, LPT, THREADS, true><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
-    else optimize_kernel<S, LPT, THREADS, false><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    if (dp.mem == FASTMEM) {
+        if (pl.psmem) optimize_kernel<S, LPT, THREADS, true, FASTMEM><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+        else optimize_kernel<S, LPT, THREADS, false, FASTMEM><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    } else {
+        if (pl.psmem) optimize_kernel<S, LPT, THREADS, true, 0><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+        else optimize_kernel<S, LPT, THREADS, false, 0><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    }
     return ok(cudaGetLastError());
 }
 

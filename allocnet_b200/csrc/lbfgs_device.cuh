@@ -21,6 +21,9 @@
 #ifndef MINCOB_LOCKSTEP
 #define MINCOB_LOCKSTEP 0
 #endif
+#ifndef MINCOB_HDEP
+#define MINCOB_HDEP 2   // (s, y) pairs of the two-loop recursion in flight ahead of their use (MEM > 0 kernels)
+#endif
 #ifndef MINCOB_MINB
 #define MINCOB_MINB 2   // resident blocks per SM the optimize kernel is compiled for (register cap)
 #endif
@@ -124,12 +127,16 @@ __host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m
 // 32*N-byte read for the group (they are read 3x17x16 times per evaluation, ~400 evaluations per
 // problem), head/tail states, alpha / y.s / past-f rings.  The (s, y) history (touched once per
 // iteration) lives in a global scratch slab per resident group, which stays in L2.
-template <int S, int LPT, int THREADS, bool PSMEM>
+// MEM > 0: the history depth is the compile-time constant MEM (== P.mem, the launcher checks): the two-loop
+// recursion is unrolled over registers and all its history loads are issued at once, right after the
+// evaluation, so their L2 latency is covered by the reductions and the scalar decisions instead of being
+// paid slot by slot.  MEM == 0: any depth, rolled loops with two slots in flight.
+template <int S, int LPT, int THREADS, bool PSMEM, int MEM>
 __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const DevParams P, const BatchArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lig = (threadIdx.x & 31) % LPT;
     const int gib = threadIdx.x / LPT;
-    const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = P.mem, past = P.past;
+    const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = MEM > 0 ? MEM : P.mem, past = P.past;
     const int rounds = N > 2 ? N - 2 : 0;   // lane-to-lane sweeps of the block solve (warp-uniform)
 
     extern __shared__ __align__(32) double smem[];
@@ -260,6 +267,28 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             bracketed = park_i[5] & 1; touched = (park_i[5] & 2) != 0; prob = park_i[6];
         }
 #endif
+        // (s, y) pairs the two-loop recursion will want if this trial point is accepted: after the update the
+        // i-th newest pair (i >= 1) sits in slot end - i of the ring as it is now; pair 0 is the one about to be
+        // computed.  The first HDEP of them are requested here, so that the reductions and scalar decisions
+        // below cover their L2 latency; the rest follow HDEP steps ahead of their use (all of them at once
+        // would not fit in registers next to x, g, xp, gp, d).  Slots never written yet (bound < m) hold
+        // garbage that the `i < bound` predicates keep out.
+        struct Pair { double4 s, y; double rys; };
+        constexpr int HDEP = MEM > 1 ? (MINCOB_HDEP < MEM - 1 ? MINCOB_HDEP : MEM - 1) : 0;
+        const int end0 = end;
+        auto fetch_nth = [&](int i) {          // i-th newest pair after the update, 1 <= i < MEM
+            int jj = end0 - i;
+            jj = jj < 0 ? jj + MEM : jj;
+            const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)jj * LPT * 8);
+            Pair p;
+            p.s = slot[0]; p.y = slot[1]; p.rys = ysv[jj];
+            return p;
+        };
+        Pair hq[MEM > 1 ? MEM : 2];            // hq[i] = i-th newest (hq[0] = the new pair)
+        if (MEM > 1) {
+#pragma unroll
+            for (int i = 1; i <= HDEP; ++i) hq[i] = fetch_nth(i);
+        }
 
         // ---- reductions every group may need ------------------------------------------------------
         const double gn = ginf<LPT>(FULL, g), xn = ginf<LPT>(FULL, x);
@@ -358,61 +387,99 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 start_ls = true;
             }
             __syncwarp();
-            const int nb = __reduce_max_sync(FULL, two ? bound : 0);
-            // The history sits in L2 (a 4 KB slab per trajectory, too big for what shared memory is left),
-            // every address of the recursion is known before it starts, and each step is a short dependent
-            // chain: keep two slots in flight ahead of the one being consumed.
-            // Backward pass, step i uses slot end-1-i (newest first); step 0 is the pair just computed.
-            struct Pair { double4 s, y; };
-            auto slot_at = [&](int i) {          // i-th newest slot of this group (i < m)
-                int jj = end - 1 - i;
-                return jj < 0 ? jj + m : jj;
-            };
-            auto fetch = [&](int jj) {
-                const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)jj * LPT * 8);
-                Pair p;
-                p.s = slot[0]; p.y = slot[1];
-                return p;
-            };
-            Pair cur, n1;
-            cur.s = make_double4(sv[0], sv[1], sv[2], sv[3]);
-            cur.y = make_double4(yv[0], yv[1], yv[2], yv[3]);
-            n1 = fetch(slot_at(nb > 1 ? 1 : 0));
-#pragma unroll 1
-            for (int i = 0; i < nb; ++i) {
-                const bool on = two && i < bound;
-                const Pair n2 = fetch(slot_at(i + 2 < nb ? i + 2 : nb - 1));
-                const int j = slot_at(i);
-                const double sj[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w};
-                const double aj = gdot<LPT>(FULL, sj, d) * ysv[j];
-                if (on) {
-                    if (lig == 0) alpha[j] = aj;
-                    d[0] -= aj * cur.y.x; d[1] -= aj * cur.y.y; d[2] -= aj * cur.y.z; d[3] -= aj * cur.y.w;
-                }
-                cur = n1; n1 = n2;
-            }
-            __syncwarp();
-            if (two) {
-                const double sc0 = ys / yy;
+            if (MEM > 0) {
+                // HKEEP: pairs >= HKEEP stay in registers from the backward pass for the forward pass (which
+                // starts with the oldest); the younger ones are requested again HDEP steps before their turn.
+                constexpr int HKEEP = MEM - HDEP > 1 ? MEM - HDEP : 1;
+                hq[0].s = make_double4(sv[0], sv[1], sv[2], sv[3]);
+                hq[0].y = make_double4(yv[0], yv[1], yv[2], yv[3]);
+                hq[0].rys = 1.0 / ys;
+                double al[MEM > 0 ? MEM : 1];
+                // backward pass, newest pair first (lbfgs.hpp:676-687)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) d[u] *= sc0;
-            }
-            // Forward pass, step i uses this group's (bound-1-i)-th newest slot (oldest first).
-            auto fwd_at = [&](int i) { return slot_at(bound - 1 - i > 0 ? bound - 1 - i : 0); };
-            cur = fetch(fwd_at(0));
-            n1 = fetch(fwd_at(1));
-#pragma unroll 1
-            for (int i = 0; i < nb; ++i) {
-                const bool on = two && i < bound;
-                const Pair n2 = fetch(fwd_at(i + 2));
-                const int j = fwd_at(i);
-                const double yj[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
-                const double beta = gdot<LPT>(FULL, yj, d) * ysv[j];
-                if (on) {
-                    const double cf = alpha[j] - beta;
-                    d[0] += cf * cur.s.x; d[1] += cf * cur.s.y; d[2] += cf * cur.s.z; d[3] += cf * cur.s.w;
+                for (int i = 0; i < MEM; ++i) {
+                    if (i >= 1 && i + HDEP < MEM) hq[i + HDEP] = fetch_nth(i + HDEP);
+                    const bool on = two && i < bound;
+                    const double sj[4] = {hq[i].s.x, hq[i].s.y, hq[i].s.z, hq[i].s.w};
+                    const double aj = gdot<LPT>(FULL, sj, d) * hq[i].rys;
+                    al[i] = aj;
+                    if (on) { d[0] -= aj * hq[i].y.x; d[1] -= aj * hq[i].y.y; d[2] -= aj * hq[i].y.z; d[3] -= aj * hq[i].y.w; }
                 }
-                cur = n1; n1 = n2;
+                if (two) {
+                    const double sc0 = ys / yy;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) d[u] *= sc0;
+                }
+                // forward pass, oldest pair first (:691-701)
+                Pair hr[MEM > 1 ? MEM : 2];        // re-requested young pairs, hr[i] = i-th newest (1 <= i < HKEEP)
+#pragma unroll
+                for (int i = MEM - 1; i >= 0; --i) {
+                    if (i - HDEP >= 1) hr[i - HDEP] = fetch_nth(i - HDEP);
+                    const Pair &h = (i >= HKEEP || i == 0) ? hq[i] : hr[i];
+                    const bool on = two && i < bound;
+                    const double yj[4] = {h.y.x, h.y.y, h.y.z, h.y.w};
+                    const double beta = gdot<LPT>(FULL, yj, d) * h.rys;
+                    if (on) {
+                        const double cf = al[i] - beta;
+                        d[0] += cf * h.s.x; d[1] += cf * h.s.y; d[2] += cf * h.s.z; d[3] += cf * h.s.w;
+                    }
+                }
+            } else {
+                const int nb = __reduce_max_sync(FULL, two ? bound : 0);
+                // The history sits in L2 (a 4 KB slab per trajectory, too big for what shared memory is left),
+                // every address of the recursion is known before it starts, and each step is a short dependent
+                // chain: keep two slots in flight ahead of the one being consumed.
+                // Backward pass, step i uses slot end-1-i (newest first); step 0 is the pair just computed.
+                auto slot_at = [&](int i) {          // i-th newest slot of this group (i < m)
+                    int jj = end - 1 - i;
+                    return jj < 0 ? jj + m : jj;
+                };
+                auto fetch = [&](int jj) {
+                    const double4 *slot = reinterpret_cast<const double4 *>(hist + (size_t)jj * LPT * 8);
+                    Pair p;
+                    p.s = slot[0]; p.y = slot[1];
+                    return p;
+                };
+                Pair cur, n1;
+                cur.s = make_double4(sv[0], sv[1], sv[2], sv[3]);
+                cur.y = make_double4(yv[0], yv[1], yv[2], yv[3]);
+                n1 = fetch(slot_at(nb > 1 ? 1 : 0));
+#pragma unroll 1
+                for (int i = 0; i < nb; ++i) {
+                    const bool on = two && i < bound;
+                    const Pair n2 = fetch(slot_at(i + 2 < nb ? i + 2 : nb - 1));
+                    const int j = slot_at(i);
+                    const double sj[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w};
+                    const double aj = gdot<LPT>(FULL, sj, d) * ysv[j];
+                    if (on) {
+                        if (lig == 0) alpha[j] = aj;
+                        d[0] -= aj * cur.y.x; d[1] -= aj * cur.y.y; d[2] -= aj * cur.y.z; d[3] -= aj * cur.y.w;
+                    }
+                    cur = n1; n1 = n2;
+                }
+                __syncwarp();
+                if (two) {
+                    const double sc0 = ys / yy;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) d[u] *= sc0;
+                }
+                // Forward pass, step i uses this group's (bound-1-i)-th newest slot (oldest first).
+                auto fwd_at = [&](int i) { return slot_at(bound - 1 - i > 0 ? bound - 1 - i : 0); };
+                cur = fetch(fwd_at(0));
+                n1 = fetch(fwd_at(1));
+#pragma unroll 1
+                for (int i = 0; i < nb; ++i) {
+                    const bool on = two && i < bound;
+                    const Pair n2 = fetch(fwd_at(i + 2));
+                    const int j = fwd_at(i);
+                    const double yj[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
+                    const double beta = gdot<LPT>(FULL, yj, d) * ysv[j];
+                    if (on) {
+                        const double cf = alpha[j] - beta;
+                        d[0] += cf * cur.s.x; d[1] += cf * cur.s.y; d[2] += cf * cur.s.z; d[3] += cf * cur.s.w;
+                    }
+                    cur = n1; n1 = n2;
+                }
             }
         }
 
