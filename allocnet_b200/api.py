@@ -32,7 +32,7 @@ SYMBOLS = [
     "mincob_optimize", "mincob_optimize_device", "mincob_last_kernel_ms", "mincob_minco_forward",
     "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
-    "mincob_check_feasibility", "mincob_check_feasibility_device",
+    "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
     L.mincob_host_free.argtypes = [_vp]
     L.mincob_check_feasibility.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_check_feasibility_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
+    L.mincob_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -236,6 +237,12 @@ class MincoBatch:
 
     def check_feasibility_device(self, coeffs, T, samples, report):
         self._check(self.L.mincob_check_feasibility_device(self.h, _dev_ptr(coeffs), _dev_ptr(T), int(samples), _dev_ptr(report)))
+
+    def measure_fp64_peak(self) -> float:
+        """TFLOP/s of independent DFMA chains on this device (the fp64-pipe ceiling bench.py reports against)."""
+        v = C.c_double(0.0)
+        self._check(self.L.mincob_measure_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     # -- multi-GPU ---------------------------------------------------------------------------
     def nccl_unique_id(self) -> bytes:

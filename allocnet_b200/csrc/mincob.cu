@@ -569,6 +569,60 @@ int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double
     return 0;
 }
 
+// ---- measured fp64 ceiling --------------------------------------------------------------------
+// Independent DFMA chains on every SM: the fp64-pipe throughput this device sustains, measured with CUDA
+// events on the handle's stream.  bench.py divides the optimize kernel's fp64 flop rate by it (the HBM
+// roofline BASELINE.json names does not bind this path).
+namespace {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters, double a, double b) {
+    constexpr int CH = 8;
+    double x[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) x[c] = 1.0e-3 * (threadIdx.x + c);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) x[c] = fma(x[c], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s += x[c];
+    if (s == 123.456) sink[0] = s;   // never true: keeps the chains alive
+}
+}  // namespace
+
+int mincob_measure_fp64_peak(mincob_handle h, double *tflops) {
+    if (!h || !tflops) return MINCOB_E_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    double *sink = nullptr;
+    CU(h, cudaMalloc((void **)&sink, sizeof(double)));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 20000;
+    cudaEvent_t e0, e1;
+    CU(h, cudaEventCreate(&e0));
+    CU(h, cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {          // first pass warms up, best of the next three
+        cudaEventRecord(e0, h->stream);
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(sink, iters, 0.999999, 1.0e-6);
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+            return fail(h, MINCOB_E_CUDA, "fp64_peak_kernel: %s", cudaGetErrorString(e));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    const double flops = 2.0 * 8 * 4 * (double)iters * threads * blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return 0;
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------
 int mincob_nccl_unique_id(void *uid) {
     if (!uid) return MINCOB_E_INVALID;

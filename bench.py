@@ -328,14 +328,24 @@ def main():
         except Exception:
             peak = 6650.0
         achieved = alg / (k_ms * 1e-3) / 1e9
-        traffic = None
-        try:  # dram bytes of one launch from the committed `ncu --set full` capture, if any
+        traffic, fp64 = None, None
+        try:  # dram bytes and fp64 flops of one launch from the committed `ncu --set full` capture, if any
             with open(os.path.join(ROOT, "profiles", "optimize_kernel_traffic.json")) as fh:
                 tj = json.load(fh)
-            if tj.get("batch") == B and tj.get("pieces") == N and tj.get("K") == K:
+            if tj.get("batch") == B and tj.get("pieces") == N and tj.get("K") == K and tj.get("S", 3) == S:
                 traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+                if tj.get("fp64_flops_per_eval"):
+                    # what actually bounds the kernel: executed fp64 flops (2 per DFMA, 1 per DADD/DMUL, predicated-on
+                    # threads only; counted by ncu per evaluation for this configuration) over the live kernel time,
+                    # against the DFMA rate measured on this device a moment ago
+                    fl = float(tj["fp64_flops_per_eval"]) * evals_sum
+                    pk = mb.measure_fp64_peak()
+                    fp64 = {"bound": "fp64", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                            "frac": fl / (k_ms * 1e-3) / 1e12 / pk, "flops_per_eval": float(tj["fp64_flops_per_eval"]),
+                            "peak_source": "mincob_measure_fp64_peak (independent DFMA chains, CUDA events, this run)",
+                            "flops_source": tj.get("source")}
+        except Exception as e:
+            print(f"[bench] no traffic / fp64 record: {e}", file=sys.stderr)
         line = {
             "metric": METRIC, "value": world * B * a.steps / (ms_tot * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_tot / a.steps, "higher_is_better": True,
@@ -357,6 +367,8 @@ def main():
             "gpu_launches": a.steps,
             "clocks": clk,
         }
+        if fp64 is not None:
+            line["roofline_fp64"] = fp64
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not a.no_cpu:

@@ -136,6 +136,11 @@ int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double
 int mincob_check_feasibility_device(mincob_handle h, const double *coeffs_d, const double *T_d, int samples,
                                     double *report_d);
 
+/* ---- measured fp64 ceiling of the device: independent DFMA chains on every SM, timed with CUDA events on the
+ *      handle's stream; TFLOP/s (2 flop per DFMA).  No counterpart in the reference (a CPU library); bench.py
+ *      reports the optimize kernel's fp64 flop rate against it next to the HBM roofline. */
+int mincob_measure_fp64_peak(mincob_handle h, double *tflops);
+
 /* ---- multi-GPU: one process per GPU, problems block-partitioned, ONE all-gather of the solved
  *      coefficients (BASELINE.json north_star).  unique_id is the 128-byte ncclUniqueId made
  *      on rank 0 by mincob_nccl_unique_id and broadcast by the caller (torch.distributed). */

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round record: GPU parity tests, both bench arms, ncu launch list + full capture of optimize_kernel, sanitizer.
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench reference rc=$?"; cat gpurun_out/bench_reference.json
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches.log 2>&1; echo "ncu launch list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:optimize_kernel -s 3 -c 1 -f -o gpurun_out/prof_optimize python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+if [ -n "$SANITIZE" ]; then bash tools/gpu_sanity.sh; fi
