@@ -33,6 +33,7 @@ SYMBOLS = [
     "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
+    "mincob_max_rates", "mincob_max_rates_device",
 ]
 
 
@@ -80,6 +81,8 @@ def load_library() -> C.CDLL:
     L.mincob_check_feasibility.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_check_feasibility_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
+    L.mincob_max_rates.argtypes = [_vp, _vp, _vp, _vp]
+    L.mincob_max_rates_device.argtypes = [_vp, _vp, _vp, _vp]
     _lib = L
     return L
 
@@ -237,6 +240,16 @@ class MincoBatch:
 
     def check_feasibility_device(self, coeffs, T, samples, report):
         self._check(self.L.mincob_check_feasibility_device(self.h, _dev_ptr(coeffs), _dev_ptr(T), int(samples), _dev_ptr(report)))
+
+    def max_rates(self, coeffs, T):
+        """[B][3] exact max |v|, |a|, |j| per trajectory (Trajectory<D>::getMaxVelRate / getMaxAccRate, + jerk)."""
+        coeffs = _f64(coeffs); T = _f64(T)
+        rates = np.empty((coeffs.shape[0], 3), dtype=np.float64)
+        self._check(self.L.mincob_max_rates(self.h, _np_ptr(coeffs), _np_ptr(T), _np_ptr(rates)))
+        return rates
+
+    def max_rates_device(self, coeffs, T, rates):
+        self._check(self.L.mincob_max_rates_device(self.h, _dev_ptr(coeffs), _dev_ptr(T), _dev_ptr(rates)))
 
     def measure_fp64_peak(self) -> float:
         """TFLOP/s of independent DFMA chains on this device (the fp64-pipe ceiling bench.py reports against)."""

@@ -77,4 +77,13 @@ struct CheckArgs {
     double *out;                   // [B][4]: max |v|, max |a|, max |j|, max_k (n_k.p + d_k)  (<= 0: inside the corridor)
 };
 
+// exact maxima of |v|, |a|, |j| over optimized trajectories: the answers of Piece<D>::getMaxVelRate / getMaxAccRate
+// and Trajectory<D>::getMaxVelRate / getMaxAccRate (gcopter/trajectory.hpp:177-273, 598-622), by bracketing and
+// bisecting the stationary points of |p^(d)(t)|^2 instead of Sturm isolation
+struct RateArgs {
+    int B, N, grid;                // `grid` bracketing sub-intervals per piece
+    const double *coeffs, *T;      // [B][N][3][2S] Trajectory order, [B][N]
+    double *out;                   // [B][3]: max |v|, max |a|, max |j|
+};
+
 }  // namespace mincob

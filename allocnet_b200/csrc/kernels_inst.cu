@@ -138,6 +138,81 @@ __global__ void __launch_bounds__(THREADS) check_kernel(const CheckArgs a) {
     }
 }
 
+// ---- exact rate maxima: one lane per piece ----------------------------------------------------------------
+// q_d(t) = |p^(d)(t)|^2 on [0, T] has its maximum at an end point or where q_d' = 2 p^(d).p^(d+1) vanishes.  The
+// reference forms q_d' in monomial form and isolates its roots with Sturm sequences (root_finder.hpp, tolerance
+// FLT_EPSILON / T); here every lane walks `grid` sub-intervals of its piece, keeps the largest q_d seen, and
+// wherever p^(d).p^(d+1) changes sign bisects the bracket to the last bit and takes q_d there.  Two stationary
+// points inside one sub-interval (1/grid of a piece) are seen only through the grid values; with grid = 128 that
+// is far below the reference's own tolerance for trajectories an optimizer produces.
+template <int D>
+__device__ __forceinline__ void deriv3(const double *c, double t, int d, double (&r)[3]) {
+    // d-th derivative of the three axis polynomials; c[x*D + k] multiplies t^(D-1-k) (trajectory.hpp:75-133)
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        double acc = 0.0;
+        for (int k = 0; k < D - d; ++k) {
+            double f = 1.0;
+            for (int u = 0; u < d; ++u) f *= (double)(D - 1 - k - u);
+            acc = fma(acc, t, c[x * D + k] * f);
+        }
+        r[x] = acc;
+    }
+}
+template <int S, int LPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) maxrate_kernel(const RateArgs a) {
+    constexpr int D = 2 * S;
+    const int lig = (threadIdx.x & 31) % LPT;
+    const unsigned mask = 0xffffffffu;
+    const int N = a.N;
+    const int groups = gridDim.x * (THREADS / LPT);
+    const int rounds = (a.B + groups - 1) / groups;
+    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    for (int it = 0; it < rounds; ++it, p += groups) {
+        const bool live = p < a.B && lig < N;
+        double best[3] = {0.0, 0.0, 0.0};
+        if (live) {
+            double c[3 * D];
+#pragma unroll
+            for (int i = 0; i < 3 * D; ++i) c[i] = a.coeffs[((size_t)p * N + lig) * 3 * D + i];
+            const double T = a.T[(size_t)p * N + lig];
+            for (int d = 1; d <= 3; ++d) {
+                double bq = 0.0, tp = 0.0, gp = 0.0;
+                for (int i = 0; i <= a.grid; ++i) {
+                    const double t = (i == a.grid) ? T : T * i / a.grid;
+                    double r[3], rn[3];
+                    deriv3<D>(c, t, d, r);
+                    deriv3<D>(c, t, d + 1, rn);
+                    const double g = r[0] * rn[0] + r[1] * rn[1] + r[2] * rn[2];
+                    bq = fmax(bq, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                    if (i > 0 && ((gp < 0.0) != (g < 0.0)) && gp != 0.0 && g != 0.0) {
+                        double lo = tp, hi = t;
+                        const bool lo_neg = gp < 0.0;
+                        for (int b = 0; b < 64; ++b) {
+                            const double mid = 0.5 * (lo + hi);
+                            if (!(lo < mid && mid < hi)) break;
+                            deriv3<D>(c, mid, d, r);
+                            deriv3<D>(c, mid, d + 1, rn);
+                            const double gm = r[0] * rn[0] + r[1] * rn[1] + r[2] * rn[2];
+                            if ((gm < 0.0) == lo_neg && gm != 0.0) lo = mid; else hi = mid;
+                        }
+                        deriv3<D>(c, 0.5 * (lo + hi), d, r);
+                        bq = fmax(bq, r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                    }
+                    tp = t; gp = g;
+                }
+                best[d - 1] = bq;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) best[d] = group_max<LPT>(mask, best[d]);
+        if (p < a.B && lig == 0) {
+            double *o = a.out + (size_t)p * 3;
+            o[0] = sqrt(best[0]); o[1] = sqrt(best[1]); o[2] = sqrt(best[2]);
+        }
+    }
+}
+
 }  // namespace mincob
 
 namespace {
@@ -248,7 +323,15 @@ LaunchResult launch_check(cudaStream_t st, int sm_count, const CheckArgs &a) {
     return ok(cudaGetLastError());
 }
 
-const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco, optimize_scratch, launch_check};
+LaunchResult launch_maxrates(cudaStream_t st, int sm_count, const RateArgs &a) {
+    int blocks = (a.B + GPB - 1) / GPB;
+    const int cap = sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    maxrate_kernel<S, LPT, THREADS><<<blocks, THREADS, 0, st>>>(a);
+    return ok(cudaGetLastError());
+}
+
+const LaunchTable kTable = {launch_evaluate, launch_optimize, launch_minco, optimize_scratch, launch_check, launch_maxrates};
 }  // namespace
 
 #define MINCOB_CAT_(a, b, c) mincob_table_##a##_##b

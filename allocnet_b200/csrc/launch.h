@@ -17,6 +17,7 @@ struct LaunchTable {
     // bytes of global scratch (L-BFGS history slabs) `optimize` needs in BatchArgs::hist
     size_t (*optimize_scratch)(int sm_count, const DevParams &, const BatchArgs &);
     LaunchResult (*check)(cudaStream_t, int sm_count, const CheckArgs &);
+    LaunchResult (*maxrates)(cudaStream_t, int sm_count, const RateArgs &);
 };
 }  // namespace mincob
 const mincob::LaunchTable *mincob_table_3_8();

@@ -569,6 +569,33 @@ int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double
     return 0;
 }
 
+int mincob_max_rates_device(mincob_handle h, const double *coeffs, const double *T, double *rates) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!coeffs || !T || !rates) return fail(h, MINCOB_E_INVALID, "coeffs, T, rates must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    RateArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = h->B; a.N = h->N; a.grid = 128;
+    a.coeffs = coeffs; a.T = T; a.out = rates;
+    return launched(h, table_for(h->prm.S, a.N)->maxrates(h->stream, h->sm_count, a), "maxrate_kernel");
+}
+
+int mincob_max_rates(mincob_handle h, const double *coeffs, const double *T, double *rates) {
+    int rc = have_problems(h);
+    if (rc) return rc;
+    if (!coeffs || !T || !rates) return fail(h, MINCOB_E_INVALID, "coeffs, T, rates must be non-null");
+    CU(h, cudaSetDevice(h->device));
+    const size_t nc = (size_t)h->B * h->N * 3 * 2 * h->prm.S * sizeof(double), nt = (size_t)h->B * h->N * sizeof(double);
+    const size_t nr = (size_t)h->B * 3 * sizeof(double);
+    if ((rc = up(h, h->b_coeffs, coeffs, nc)) || (rc = up(h, h->b_T, T, nt)) || (rc = ensure(h, h->b_m0, nr))) return rc;
+    if ((rc = mincob_max_rates_device(h, (const double *)h->b_coeffs.p, (const double *)h->b_T.p, (double *)h->b_m0.p)))
+        return rc;
+    if ((rc = down(h, rates, h->b_m0, nr))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 // ---- measured fp64 ceiling --------------------------------------------------------------------
 // Independent DFMA chains on every SM: the fp64-pipe throughput this device sustains, measured with CUDA
 // events on the handle's stream.  bench.py divides the optimize kernel's fp64 flop rate by it (the HBM

@@ -268,7 +268,14 @@ def main():
     mb.check_feasibility_device(d_coeffs, d_T, 32, d_rep)
     torch.cuda.synchronize(dev)
     rep = d_rep.cpu().numpy()
+    d_rates = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    mb.max_rates_device(d_coeffs, d_T, d_rates)                        # exact maxima (Trajectory::getMaxVelRate ...)
+    torch.cuda.synchronize(dev)
+    rates = d_rates.cpu().numpy()
     quality = {"samples_per_piece": 33,
+               "exact_v_within_2pct": float((rates[:, 0] <= 1.02 * float(prm.v_max)).mean()),
+               "exact_a_within_2pct": float((rates[:, 1] <= 1.02 * float(prm.a_max)).mean()),
+               "exact_max_speed_p99": float(np.percentile(rates[:, 0], 99)),
                "v_within_2pct": float((rep[:, 0] <= 1.02 * float(prm.v_max)).mean()),
                "a_within_2pct": float((rep[:, 1] <= 1.02 * float(prm.a_max)).mean()),
                "j_within_2pct": float((rep[:, 2] <= 1.02 * float(prm.j_max)).mean()),

@@ -136,6 +136,16 @@ int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double
 int mincob_check_feasibility_device(mincob_handle h, const double *coeffs_d, const double *T_d, int samples,
                                     double *report_d);
 
+/* ---- exact rate maxima of optimized trajectories: per trajectory, what Trajectory<D>::getMaxVelRate /
+ *      getMaxAccRate (gcopter/trajectory.hpp:598-622; per piece :177-273, which isolate the roots of
+ *      d/dt |p^(d)|^2 with RootFinder::solvePolynomial) return, plus the same for jerk.  The device brackets the
+ *      stationary points on 128 sub-intervals per piece and bisects them.  checkMaxVelRate(v) / checkMaxAccRate(a)
+ *      (:275-313, :624-646) are `rates[b][0] < v` / `rates[b][1] < a`.
+ *      coeffs [B][N][3][2S] and T [B][N] as returned by mincob_optimize (B, N of the current
+ *      mincob_set_problems call);  rates [B][3] = max |v|, max |a|, max |j|. */
+int mincob_max_rates(mincob_handle h, const double *coeffs, const double *T, double *rates);
+int mincob_max_rates_device(mincob_handle h, const double *coeffs_d, const double *T_d, double *rates_d);
+
 /* ---- measured fp64 ceiling of the device: independent DFMA chains on every SM, timed with CUDA events on the
  *      handle's stream; TFLOP/s (2 flop per DFMA).  No counterpart in the reference (a CPU library); bench.py
  *      reports the optimize kernel's fp64 flop rate against it next to the HBM roofline. */

@@ -1,9 +1,8 @@
 // ============================================================================
 // oracle/ref_trajectory.cpp -- C wrapper around the REFERENCE's own Piece<D> / Trajectory<D>.
 // TEST INFRASTRUCTURE ONLY.  `#include "gcopter/trajectory.hpp"` resolves to the unmodified file under
-// /root/reference/src/planner/include (oracle/Makefile); <Eigen/Eigen> is oracle/eigen_shim and
-// "gcopter/root_finder.hpp" is oracle/ref_stubs (the max-rate members that need it are never
-// instantiated).  Output: oracle/_ref/libref_lbfgs.so.  It pins the OUTPUT CONTRACT of the hot path:
+// /root/reference/src/planner/include (oracle/Makefile), and so does the "gcopter/root_finder.hpp" it includes
+// (Sturm root isolation behind getMaxVelRate / checkMaxVelRate ...); <Eigen/Eigen> is oracle/eigen_shim.  Output: oracle/_ref/libref_lbfgs.so.  It pins the OUTPUT CONTRACT of the hot path:
 // coefficients in the library's Trajectory order, fed to the reference's emplace_back(dur, cMat), must
 // evaluate (getPos/getVel/getAcc/getJer), locate (locatePieceIdx) and cost (getTrajCost) as the
 // reference says -- in particular E_MINCO == 2 * getTrajCost(3) (trajectory.hpp:396-420).
@@ -39,5 +38,10 @@ void ref_traj5_positions(void *p, double *out /* [N+1][3] */) {
         for (int a = 0; a < 3; ++a) out[3 * i + a] = P(a, i);
 }
 int ref_traj5_locate(void *p, double *t_inout) { return static_cast<Trajectory<5> *>(p)->locatePieceIdx(*t_inout); }
+// max-rate members (trajectory.hpp:598-646; per piece :177-313) with the reference's own gcopter/root_finder.hpp
+double ref_traj5_max_vel_rate(void *p) { return static_cast<Trajectory<5> *>(p)->getMaxVelRate(); }
+double ref_traj5_max_acc_rate(void *p) { return static_cast<Trajectory<5> *>(p)->getMaxAccRate(); }
+int ref_traj5_check_max_vel_rate(void *p, double v) { return static_cast<Trajectory<5> *>(p)->checkMaxVelRate(v) ? 1 : 0; }
+int ref_traj5_check_max_acc_rate(void *p, double a) { return static_cast<Trajectory<5> *>(p)->checkMaxAccRate(a) ? 1 : 0; }
 
 }  // extern "C"

@@ -382,3 +382,65 @@ def test_fp64_peak_measurement_is_plausible(handles):
     (ncu: sm__sass_thread_inst_executed_op_dfma_pred_on peak_sustained), ~37 TFLOP/s at 1.96 GHz."""
     tf = handles[3].measure_fp64_peak()
     assert 20.0 < tf < 45.0, tf
+
+
+def _dense_rates(coeffs, T, pts=40001):
+    want = np.zeros(3)
+    for i in range(coeffs.shape[0]):
+        t = np.linspace(0.0, T[i], pts)
+        for d in (1, 2, 3):
+            v = np.stack([np.polyval(np.polyder(coeffs[i, a], d), t) for a in range(3)])
+            want[d - 1] = max(want[d - 1], np.sqrt((v * v).sum(axis=0).max()))
+    return want
+
+
+def test_exact_max_rates(handles, oracle):
+    """mincob_max_rates against the REFERENCE's Trajectory<5>::getMaxVelRate / getMaxAccRate (trajectory.hpp and
+    root_finder.hpp compiled verbatim, oracle/_ref; its root tolerance is FLT_EPSILON / T) and, for all three rates and
+    also without oracle/_ref, against a dense sampling; checkMaxVelRate / checkMaxAccRate are `rate < limit`."""
+    import ctypes as C
+    B, N = 96, 8
+    pb = synth.make_problems(B, N=N, K=16, S=3)
+    mb = handles[3]
+    mb.set_params(default_params(3))
+    mb.set_problems(pb)
+    res = mb.optimize(pb.x0())
+    rates = mb.max_rates(res["coeffs"], res["T"])
+    assert rates.shape == (B, 3) and np.isfinite(rates).all()
+    # never below the sampled report of the same trajectories
+    rep = mb.check_feasibility(res["coeffs"], res["T"], samples=64)
+    assert (rates >= rep[:, :3] * (1.0 - 1e-12)).all()
+    for b in range(0, B, 5):
+        np.testing.assert_allclose(rates[b], _dense_rates(res["coeffs"][b], res["T"][b]), rtol=1e-7)
+    ref = oracle.ref
+    if ref is not None and hasattr(ref, "ref_traj5_max_vel_rate"):
+        dp = C.POINTER(C.c_double)
+        ref.ref_traj5_create.restype = C.c_void_p; ref.ref_traj5_create.argtypes = [C.c_int, dp, dp]
+        ref.ref_traj5_destroy.argtypes = [C.c_void_p]
+        for fn in (ref.ref_traj5_max_vel_rate, ref.ref_traj5_max_acc_rate):
+            fn.restype = C.c_double; fn.argtypes = [C.c_void_p]
+        for fn in (ref.ref_traj5_check_max_vel_rate, ref.ref_traj5_check_max_acc_rate):
+            fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_double]
+        for b in range(B):
+            c = np.ascontiguousarray(res["coeffs"][b]); T = np.ascontiguousarray(res["T"][b])
+            h = ref.ref_traj5_create(N, T.ctypes.data_as(dp), c.ctypes.data_as(dp))
+            try:
+                assert abs(ref.ref_traj5_max_vel_rate(h) - rates[b, 0]) <= 1e-8 * rates[b, 0]
+                assert abs(ref.ref_traj5_max_acc_rate(h) - rates[b, 1]) <= 1e-8 * rates[b, 1]
+                for lim in (4.0, 4.1, 3.9):
+                    if abs(rates[b, 0] - lim) > 1e-6:
+                        assert bool(ref.ref_traj5_check_max_vel_rate(h, lim)) == bool(rates[b, 0] < lim)
+                for lim in (6.0, 6.2, 5.5):
+                    if abs(rates[b, 1] - lim) > 1e-6:
+                        assert bool(ref.ref_traj5_check_max_acc_rate(h, lim)) == bool(rates[b, 1] < lim)
+            finally:
+                ref.ref_traj5_destroy(h)
+    # S = 4 (septic pieces; no reference class is instantiated for it here): dense sampling only
+    pb4 = synth.make_problems(32, N=6, K=16, S=4)
+    mb4 = handles[4]
+    mb4.set_params(default_params(4))
+    mb4.set_problems(pb4)
+    r4 = mb4.optimize(pb4.x0())
+    rt4 = mb4.max_rates(r4["coeffs"], r4["T"])
+    for b in range(0, 32, 7):
+        np.testing.assert_allclose(rt4[b], _dense_rates(r4["coeffs"][b], r4["T"][b]), rtol=1e-7)

@@ -341,3 +341,46 @@ def test_output_contract_against_reference_trajectory(oracle):
                     np.testing.assert_allclose(g, want, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(want).max()))
         finally:
             ref.ref_traj5_destroy(h)
+
+
+def _dense_rate_maxima(coeffs, T, pts=20001):
+    """max |p'|, |p''|, |p'''| per trajectory by dense sampling (coeffs [N][3][6] descending, T [N])."""
+    out = np.zeros(3)
+    for i in range(coeffs.shape[0]):
+        t = np.linspace(0.0, T[i], pts)
+        for d in (1, 2, 3):
+            v = np.stack([np.polyval(np.polyder(coeffs[i, a], d), t) for a in range(3)])
+            out[d - 1] = max(out[d - 1], np.sqrt((v * v).sum(axis=0).max()))
+    return out
+
+
+def test_reference_max_rates_against_dense_sampling(oracle):
+    """The reference's own Trajectory<5>::getMaxVelRate / getMaxAccRate / checkMaxVelRate / checkMaxAccRate
+    (gcopter/trajectory.hpp:177-313, 598-646 and gcopter/root_finder.hpp, both compiled verbatim into oracle/_ref
+    against the Eigen stand-in) on optimized trajectories: equal to a dense sampling of the same polynomials, and the
+    check members flip exactly around that maximum.  This is the oracle of mincob_max_rates (GPU test)."""
+    import ctypes as C
+    ref = oracle.ref
+    if ref is None or not hasattr(ref, "ref_traj5_max_vel_rate"):
+        pytest.skip("oracle/_ref (with root_finder.hpp) not present")
+    dp = C.POINTER(C.c_double)
+    ref.ref_traj5_create.restype = C.c_void_p; ref.ref_traj5_create.argtypes = [C.c_int, dp, dp]
+    ref.ref_traj5_destroy.argtypes = [C.c_void_p]
+    for fn in (ref.ref_traj5_max_vel_rate, ref.ref_traj5_max_acc_rate):
+        fn.restype = C.c_double; fn.argtypes = [C.c_void_p]
+    for fn in (ref.ref_traj5_check_max_vel_rate, ref.ref_traj5_check_max_acc_rate):
+        fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_double]
+    B, N = 24, 5
+    pb = synth.make_problems(B, N=N, K=16, S=3)
+    res = oracle.optimize_batch(default_params(3), pb, nthreads=4)
+    for b in range(B):
+        c = np.ascontiguousarray(res["coeffs"][b]); T = np.ascontiguousarray(res["T"][b])
+        want = _dense_rate_maxima(c, T)
+        h = ref.ref_traj5_create(N, T.ctypes.data_as(dp), c.ctypes.data_as(dp))
+        try:
+            v, a = ref.ref_traj5_max_vel_rate(h), ref.ref_traj5_max_acc_rate(h)
+            assert abs(v - want[0]) <= 1e-7 * want[0] and abs(a - want[1]) <= 1e-7 * want[1], (v, a, want)
+            assert ref.ref_traj5_check_max_vel_rate(h, v * 1.001) == 1 and ref.ref_traj5_check_max_vel_rate(h, v * 0.999) == 0
+            assert ref.ref_traj5_check_max_acc_rate(h, a * 1.001) == 1 and ref.ref_traj5_check_max_acc_rate(h, a * 0.999) == 0
+        finally:
+            ref.ref_traj5_destroy(h)
