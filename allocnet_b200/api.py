@@ -33,7 +33,7 @@ SYMBOLS = [
     "mincob_minco_propagate", "mincob_nccl_unique_id", "mincob_comm_init", "mincob_allgather_device",
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
-    "mincob_max_rates", "mincob_max_rates_device",
+    "mincob_max_rates", "mincob_max_rates_device", "mincob_minco_forward_device", "mincob_minco_propagate_device",
 ]
 
 
@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
     L.mincob_check_feasibility_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
     L.mincob_max_rates.argtypes = [_vp, _vp, _vp, _vp]
+    L.mincob_minco_forward_device.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 9
+    L.mincob_minco_propagate_device.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 8
     L.mincob_max_rates_device.argtypes = [_vp, _vp, _vp, _vp]
     _lib = L
     return L
@@ -240,6 +242,17 @@ class MincoBatch:
 
     def check_feasibility_device(self, coeffs, T, samples, report):
         self._check(self.L.mincob_check_feasibility_device(self.h, _dev_ptr(coeffs), _dev_ptr(T), int(samples), _dev_ptr(report)))
+
+    def minco_forward_device(self, B, N, head, tail, inPs, ts, coeffs_asc=None, energy=None, gdC=None, gdT=None, flat=None):
+        """CUDA tensors in the layouts of minco_forward; None outputs are skipped; enqueues only."""
+        self._check(self.L.mincob_minco_forward_device(self.h, int(B), int(N), _dev_ptr(head), _dev_ptr(tail), _dev_ptr(inPs),
+                                                       _dev_ptr(ts), _dev_ptr(coeffs_asc), _dev_ptr(energy), _dev_ptr(gdC),
+                                                       _dev_ptr(gdT), _dev_ptr(flat)))
+
+    def minco_propagate_device(self, B, N, head, tail, inPs, ts, gdC, gdT, gradByPoints, gradByTimes):
+        self._check(self.L.mincob_minco_propagate_device(self.h, int(B), int(N), _dev_ptr(head), _dev_ptr(tail), _dev_ptr(inPs),
+                                                         _dev_ptr(ts), _dev_ptr(gdC), _dev_ptr(gdT), _dev_ptr(gradByPoints),
+                                                         _dev_ptr(gradByTimes)))
 
     def max_rates(self, coeffs, T):
         """[B][3] exact max |v|, |a|, |j| per trajectory (Trajectory<D>::getMaxVelRate / getMaxAccRate, + jerk)."""

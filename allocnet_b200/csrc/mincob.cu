@@ -486,6 +486,37 @@ static int down(mincob_ctx *h, void *dst, const DevBuf &b, size_t bytes) {
     return 0;
 }
 
+// device-pointer forms: enqueue on the handle's stream and return (no copies, no synchronisation)
+int mincob_minco_forward_device(mincob_handle h, int B, int N, const double *head, const double *tail, const double *inPs,
+                                const double *ts, double *coeffs_asc, double *energy, double *gdC, double *gdT, double *flat) {
+    if (!h || !head || !tail || !ts || (N > 1 && !inPs)) return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, 0);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    MincoArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.N = N;
+    a.head = head; a.tail = tail; a.inPs = inPs; a.ts = ts;
+    a.coeffs_asc = coeffs_asc; a.energy = energy; a.gdC = gdC; a.gdT = gdT; a.flat = flat;
+    return do_minco(h, a, 0);
+}
+
+int mincob_minco_propagate_device(mincob_handle h, int B, int N, const double *head, const double *tail, const double *inPs,
+                                  const double *ts, const double *gdC, const double *gdT, double *gradByPoints,
+                                  double *gradByTimes) {
+    if (!h || !head || !tail || !ts || !gdC || !gdT || !gradByTimes || (N > 1 && (!inPs || !gradByPoints)))
+        return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, 0);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    MincoArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.N = N;
+    a.head = head; a.tail = tail; a.inPs = inPs; a.ts = ts;
+    a.gdC_in = gdC; a.gdT_in = gdT; a.gradByPoints = gradByPoints; a.gradByTimes = gradByTimes;
+    return do_minco(h, a, 1);
+}
+
 int mincob_minco_forward(mincob_handle h, int B, int N, const double *head, const double *tail, const double *inPs,
                          const double *ts, double *coeffs_asc, double *energy, double *gdC, double *gdT, double *flat) {
     if (!h || !head || !tail || !ts || (N > 1 && !inPs)) return MINCOB_E_INVALID;

@@ -126,6 +126,16 @@ int mincob_minco_propagate(mincob_handle h, int B, int N, const double *head, co
                            const double *inPs, const double *ts, const double *gdC, const double *gdT,
                            double *gradByPoints, double *gradByTimes);
 
+/* Device-pointer forms of the two calls above (same layouts): enqueue one kernel on the handle's stream and
+ * return; used by the differentiable layer allocnet_b200/autograd.py (forward = setParameters + getEnergy...,
+ * backward = propogateGrad). */
+int mincob_minco_forward_device(mincob_handle h, int B, int N, const double *head_d, const double *tail_d,
+                                const double *inPs_d, const double *ts_d, double *coeffs_asc_d, double *energy_d,
+                                double *gdC_d, double *gdT_d, double *flat_d);
+int mincob_minco_propagate_device(mincob_handle h, int B, int N, const double *head_d, const double *tail_d,
+                                  const double *inPs_d, const double *ts_d, const double *gdC_d, const double *gdT_d,
+                                  double *gradByPoints_d, double *gradByTimes_d);
+
 /* ---- feasibility report of optimized trajectories: what Piece::getMaxVelRate / getMaxAccRate /
  *      checkMaxVelRate (gcopter/trajectory.hpp:177-314) answer by root finding, on a fixed grid of
  *      `samples`+1 points per piece (both ends included), plus the largest corridor residual against

@@ -444,3 +444,64 @@ def test_exact_max_rates(handles, oracle):
     rt4 = mb4.max_rates(r4["coeffs"], r4["T"])
     for b in range(0, 32, 7):
         np.testing.assert_allclose(rt4[b], _dense_rates(r4["coeffs"][b], r4["T"][b]), rtol=1e-7)
+
+
+def test_shape_and_state_validation():
+    """Error behaviour of the boundary (include/mincob.h): bad shapes are MINCOB_E_INVALID before anything is
+    launched, compute calls before set_problems are MINCOB_E_STATE, and the handle stays usable afterwards."""
+    import ctypes as C
+    mb = api.MincoBatch(default_params(3), device=0)
+    L = mb.L
+    pb = synth.make_problems(4, N=8, K=16, S=3)
+    x = pb.x0(); f = np.zeros(4); g = np.zeros_like(x)
+    E_INVALID = L.mincob_set_problems(mb.h, 0, 8, 16, api._np_ptr(pb.head), api._np_ptr(pb.tail), api._np_ptr(pb.hpolys), api._np_ptr(pb.hrows))
+    assert E_INVALID != 0 and b"B must be" in L.mincob_last_error(mb.h)            # empty batch
+    E_STATE = L.mincob_evaluate(mb.h, api._np_ptr(x), api._np_ptr(f), api._np_ptr(g))
+    assert E_STATE != 0 and E_STATE != E_INVALID                                     # nothing set yet
+    for N in (0, 33):                                                                # MINCOB_MAX_PIECES = 32
+        assert L.mincob_set_problems(mb.h, 4, N, 16, api._np_ptr(pb.head), api._np_ptr(pb.tail), api._np_ptr(pb.hpolys), api._np_ptr(pb.hrows)) == E_INVALID
+    assert L.mincob_set_problems(mb.h, 4, 8, 16, api._np_ptr(pb.head), api._np_ptr(pb.tail), None, None) == E_INVALID   # K > 0 without rows
+    assert L.mincob_set_problems(mb.h, 4, 8, 16, None, api._np_ptr(pb.tail), api._np_ptr(pb.hpolys), api._np_ptr(pb.hrows)) == E_INVALID
+    mb.set_problems(pb)                                                              # still works
+    assert L.mincob_evaluate(mb.h, None, api._np_ptr(f), api._np_ptr(g)) == E_INVALID
+    f1, g1 = mb.evaluate(x)
+    assert np.isfinite(f1).all() and np.isfinite(g1).all()
+    mb.close()
+
+
+@pytest.mark.parametrize("S,N", [(3, 5), (3, 8), (4, 4), (3, 1)])
+def test_autograd_layer_against_torch_reference(handles, S, N):
+    """allocnet_b200.autograd.minco_layer (forward = setParameters/getEnergy kernel, backward = propogateGrad kernel)
+    against torch.autograd through a plain PyTorch fp64 dense MINCO: values and the gradients of a loss that uses both
+    outputs (energy + time + a functional of the coefficients), with respect to waypoints and durations."""
+    import torch
+    from allocnet_b200.autograd import minco_layer
+    from torch_minco_ref import torch_dense_minco
+    dev = torch.device("cuda:0")
+    B = 6
+    pb = synth.make_problems(B, N=N, K=0, S=S)
+    mb = handles[S]
+    head = torch.tensor(pb.head, device=dev); tail = torch.tensor(pb.tail, device=dev)
+    g = torch.Generator().manual_seed(5)
+    q = torch.tensor(pb.q0 if N > 1 else np.zeros((B, 0, 3)), device=dev).requires_grad_(N > 1)
+    T = (torch.tensor(pb.T0, device=dev) * (0.7 + 0.6 * torch.rand(B, N, generator=g, dtype=torch.float64).to(dev))).requires_grad_(True)
+    wc = torch.randn(B, 2 * S * N, 3, generator=g, dtype=torch.float64).to(dev)
+
+    def loss_of(E, c, T):
+        return (E * torch.linspace(0.5, 1.5, B, dtype=torch.float64, device=dev)).sum() + 20.0 * T.sum() + (wc * c).sum() + 0.5 * (c * c).sum()
+    E, c = minco_layer(mb, head, tail, q, T)
+    L = loss_of(E, c, T)
+    grads = torch.autograd.grad(L, [T] + ([q] if N > 1 else []))
+    q2 = q.detach().clone().requires_grad_(N > 1); T2 = T.detach().clone().requires_grad_(True)
+    Es, cs = [], []
+    for b in range(B):
+        e, cc = torch_dense_minco(S, head[b], tail[b], q2[b], T2[b])
+        Es.append(e); cs.append(cc)
+    E2 = torch.stack(Es); c2 = torch.stack(cs)
+    L2 = loss_of(E2, c2, T2)
+    grads2 = torch.autograd.grad(L2, [T2] + ([q2] if N > 1 else []))
+    tol = 1e-9 if S == 3 else 1e-6                      # septic monomial systems are worse conditioned (DESIGN.md section 1)
+    assert float(((E - E2).abs() / E2.abs()).max().detach()) <= tol
+    assert float(((c - c2).abs().max() / c2.abs().max()).detach()) <= tol
+    for ga, gb in zip(grads, grads2):
+        assert float((ga - gb).abs().max() / gb.abs().max()) <= (1e-8 if S == 3 else 1e-5), (S, N)

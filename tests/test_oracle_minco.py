@@ -384,3 +384,26 @@ def test_reference_max_rates_against_dense_sampling(oracle):
             assert ref.ref_traj5_check_max_acc_rate(h, a * 1.001) == 1 and ref.ref_traj5_check_max_acc_rate(h, a * 0.999) == 0
         finally:
             ref.ref_traj5_destroy(h)
+
+
+@pytest.mark.parametrize("S,N", [(3, 5), (4, 4), (3, 1)])
+def test_torch_reference_equals_oracle(oracle, S, N):
+    """tests/torch_minco_ref.py (the torch.autograd reference of the differentiable layer) reproduces the oracle's
+    coefficients, energy and -- through autograd -- getEnergyPartialGradByTimes + propogateGrad of the energy."""
+    import torch
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from torch_minco_ref import torch_dense_minco
+    rng = np.random.default_rng(11)
+    head, tail, q, T = rand_problem(rng, S, N)
+    ref = oracle.minco_forward(S, head, tail, q, T)
+    tq = torch.tensor(q, dtype=torch.float64).requires_grad_(N > 1); tT = torch.tensor(T, dtype=torch.float64).requires_grad_(True)
+    E, c = torch_dense_minco(S, torch.tensor(head), torch.tensor(tail), tq, tT)
+    tol = 1e-9 if S == 3 else 1e-7
+    assert abs(float(E.detach()) - ref["energy"]) <= tol * abs(ref["energy"])
+    assert np.abs(c.detach().numpy() - ref["coeffs"]).max() <= tol * np.abs(ref["coeffs"]).max()
+    grads = torch.autograd.grad(E, [tT] + ([tq] if N > 1 else []))
+    gq, gT = oracle.minco_propagate(S, head, tail, q, T, ref["gdC"], ref["gdT"])
+    assert np.abs(grads[0].numpy() - gT).max() <= 10 * tol * np.abs(gT).max()
+    if N > 1:
+        assert np.abs(grads[1].numpy() - gq).max() <= 10 * tol * np.abs(gq).max()
