@@ -260,6 +260,9 @@ static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs 
         per_sm = dp.mem == FASTMEM ? blocks_per_sm<true, FASTMEM>(pl.smem, pl.err) : blocks_per_sm<true, 0>(pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
         pl.psmem = per_sm >= MINCOB_MINB || per_sm >= 2;
+#ifdef MINCOB_GLOBAL_PLANES   // experiment: never stage half-planes in shared memory (occupancy then depends on registers only)
+        pl.psmem = 0;
+#endif
     }
     if (!pl.psmem) {
         pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0, LPT) * sizeof(double);

@@ -505,3 +505,40 @@ def test_autograd_layer_against_torch_reference(handles, S, N):
     assert float(((c - c2).abs().max() / c2.abs().max()).detach()) <= tol
     for ga, gb in zip(grads, grads2):
         assert float((ga - gb).abs().max() / gb.abs().max()) <= (1e-8 if S == 3 else 1e-5), (S, N)
+
+
+def test_config4_pipeline_net_warm_start_on_device(handles, oracle):
+    """BASELINE.json configs[3] end to end on the device: 16-piece problems, initial durations from the batched
+    time-allocation forward (allocnet_b200/timealloc.py, run on cuda:0 over sliding 5-piece windows; weights here
+    are synthetic because the reference's model files do not travel -- tests/test_timealloc.py checks the same code
+    against the reference TorchScript model where it exists), then the optimizer from that start: cost/gradient parity
+    at the warm start (1e-9) and the same converged optimum statistics as the CPU oracle from the same start."""
+    import torch
+    from allocnet_b200 import timealloc
+    B, N, K = 192, 16, 16
+    pb = synth.make_problems(B, N=N, K=K, S=3)
+    w = timealloc.random_weights(seed=9, device="cuda:0")
+    w["tfs_output_layer.bias"] = torch.tensor([1.2], device="cuda:0")          # durations around 1.2 s, all positive
+    w["stop_token_output_layer.0.bias"] = torch.tensor([-30.0], device="cuda:0")  # never stop early
+    T0 = timealloc.warm_start_durations(w, pb, device="cuda:0")
+    assert T0.shape == (B, N) and (T0 > 0).all() and np.abs(T0 - pb.T0).max() > 1e-3   # the net's answer, not the fallback
+    import dataclasses
+    pbw = dataclasses.replace(pb, T0=T0)
+    x0 = pbw.x0()
+    prm = default_params(3, max_iterations=5000)
+    mb = handles[3]
+    mb.set_params(prm)
+    mb.set_problems(pbw)
+    f, g = mb.evaluate(x0)
+    fo, go = oracle.cost_batch(prm, pbw, x0, nthreads=8)
+    assert float(np.max(np.abs(f - fo) / np.abs(fo))) <= TOL
+    assert float(np.max(np.abs(g - go).max(axis=1) / np.abs(go).max(axis=1))) <= TOL
+    res = mb.optimize(x0)
+    ref = oracle.optimize_batch(prm, pbw, x0=x0, nthreads=8)
+    assert (res["status"] >= 0).mean() >= 0.98 and (ref["status"] >= 0).mean() >= 0.98
+    fo2, _ = oracle.cost_batch(prm, pbw, res["x"], nthreads=8)
+    assert float(np.max(np.abs(res["f"] - fo2) / np.abs(fo2))) <= TOL
+    rel = np.abs(res["f"] - ref["f"]) / np.abs(ref["f"])
+    assert np.median(rel) <= 2e-3 and np.mean(rel < 2e-2) >= 0.85, (np.median(rel), rel.max())
+    assert abs(res["evals"].mean() / ref["evals"].mean() - 1.0) <= 0.15
+    mb.set_params(default_params(3))
