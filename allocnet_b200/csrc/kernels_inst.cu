@@ -241,7 +241,10 @@ struct OptPlan {
     cudaError_t err;
 };
 // history depth the register-resident two-loop recursion is compiled for (upstream default of this build, params.py)
-constexpr int FASTMEM = 8;
+#ifndef MINCOB_FASTMEM
+#define MINCOB_FASTMEM 8
+#endif
+constexpr int FASTMEM = MINCOB_FASTMEM;   // 0: every depth takes the rolled loops (experiments)
 template <bool PSMEM, int MEM>
 static int blocks_per_sm(size_t smem, cudaError_t &e) {
     auto kern = optimize_kernel<S, LPT, THREADS, PSMEM, MEM>;

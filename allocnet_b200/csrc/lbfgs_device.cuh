@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #pragma unroll
             for (int i = 1; i <= HDEP; ++i) hq[i] = fetch_nth(i);
         }
+#ifdef MINCOB_HIST_PREFETCH
+        if (MEM == 0) {   // experiment: rolled two-loop recursion, history lines pulled towards L1 ahead of it
+#pragma unroll 1
+            for (int j = 0; j < m; ++j) {
+                const double *sl = hist + (size_t)j * LPT * 8;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sl));
+            }
+        }
+#endif
 
         // ---- reductions every group may need ------------------------------------------------------
         const double gn = ginf<LPT>(FULL, g), xn = ginf<LPT>(FULL, x);

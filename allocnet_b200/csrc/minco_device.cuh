@@ -35,6 +35,12 @@
 #ifndef MINCOB_UNROLL_JJ
 #define MINCOB_UNROLL_JJ 1   // samples per trip of the rolled phase-2 loop of penalty_piece
 #endif
+#ifndef MINCOB_JB
+#define MINCOB_JB 6          // samples whose positions phase 1 of penalty_piece holds in registers at once
+#endif
+#ifndef MINCOB_UNROLL_K
+#define MINCOB_UNROLL_K 1    // half-plane rows per trip of the phase-1 loop (2: -4 %, 4: -4 %, 8: -10 %; the kernel is code-size sensitive)
+#endif
 
 namespace mincob {
 
@@ -485,7 +491,7 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
 template <int S, int LPT, bool PSMEM, class ST>
 __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT, ST> &sp, const double *planes,
                                               int rstride, int K, double &cost, double (&G)[2 * S][3], double &gT) {
-    constexpr int D = 2 * S, JB = 6;
+    constexpr int D = 2 * S, JB = MINCOB_JB;
     const int kap = P.kappa;
     const double ikap = P.ikap, imu = P.imu;
     const double step = sp.T * ikap;
@@ -512,10 +518,10 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                     pos[jj][x] = v;
                 }
             }
-#pragma unroll 2
+            constexpr int UK = MINCOB_UNROLL_K;
+#pragma unroll UK
             for (int k = 0; k < K; ++k) {
                 const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
-#pragma unroll
                 int all = -1;
 #pragma unroll
                 for (int jj = 0; jj < JB; ++jj) {
