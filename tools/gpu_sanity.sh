@@ -13,6 +13,7 @@ for S, N, K, B in ((3, 8, 16, 96), (3, 5, 50, 40), (4, 8, 16, 40), (3, 16, 16, 2
     mb = api.MincoBatch(prm, device=0); mb.set_problems(pb)
     f, g = mb.evaluate(pb.x0()); r = mb.optimize(pb.x0())
     q = pb.q0; out = mb.minco_forward(pb.head, pb.tail, q, pb.T0)
+    rep = mb.check_feasibility(r["coeffs"], r["T"], samples=16); rates = mb.max_rates(r["coeffs"], r["T"])
     print(S, N, K, B, float(f[0]), int(r["evals"].sum()))
     mb.close()
 PY
