@@ -52,7 +52,7 @@ struct BatchArgs {
     int *status, *iters, *evals;
     int *counter;               // work queue head
     double *hist;               // optimize: (s, y) history scratch, one slab per resident group
-    double *mult;               // optimize: PCR multiplier scratch, one slab per resident block
+    double *mult;               // optimize: block-solve multiplier scratch, one slab per resident block
     double *lpark;              // optimize: parked xp/gp/d, one slab per resident block
     int planes_in_smem;         // optimize: stage each problem's half-planes in shared memory
     unsigned long long *total_evals;  // optional: sum of evaluations (for the roofline numerator)

@@ -7,10 +7,13 @@
 // cost-functional call site per loop trip so that the 32/LPT groups of a warp, each somewhere
 // else in its own line search, execute the expensive evaluation convergently.  A group that
 // finishes writes its results (x, f, status, iterations, evaluations, Trajectory-order
-// coefficients, durations) and pulls the next problem from a global counter, so there is no
-// tail of half-empty launches and no per-iteration HBM traffic for optimizer state:
-// x, g, xp, gp, d live in registers (lane i owns tau_i and q_i), the (s, y) history in
-// shared memory.
+// coefficients, durations) and pulls the next problem from a global counter, so there are no
+// half-empty launches and no per-iteration HBM traffic for optimizer state.
+// Where the state lives: x, g, xp, gp, d in registers (lane i owns tau_i and q_i; xp, gp, d and
+// the group's scalars are parked in an L2-resident slab / shared memory while the cost functional
+// runs, which is what lets three blocks share an SM); the problem's half-planes, head/tail and
+// the small rings (1/y.s, past f) in shared memory; the (s, y) history in a global slab per
+// resident group that never leaves L2.  DESIGN.md section 3 has the table.
 // ============================================================================
 #pragma once
 #include "minco_device.cuh"
@@ -128,9 +131,9 @@ __host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m
 // problem), head/tail states, alpha / y.s / past-f rings.  The (s, y) history (touched once per
 // iteration) lives in a global scratch slab per resident group, which stays in L2.
 // MEM > 0: the history depth is the compile-time constant MEM (== P.mem, the launcher checks): the two-loop
-// recursion is unrolled over registers and all its history loads are issued at once, right after the
-// evaluation, so their L2 latency is covered by the reductions and the scalar decisions instead of being
-// paid slot by slot.  MEM == 0: any depth, rolled loops with two slots in flight.
+// recursion is unrolled over registers, the first MINCOB_HDEP history pairs are requested right after the
+// evaluation (their L2 latency is covered by the reductions and the scalar decisions) and the others
+// MINCOB_HDEP steps ahead of their use.  MEM == 0: any depth, rolled loops with two slots in flight.
 template <int S, int LPT, int THREADS, bool PSMEM, int MEM>
 __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const DevParams P, const BatchArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
