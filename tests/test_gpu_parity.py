@@ -435,15 +435,43 @@ def test_exact_max_rates(handles, oracle):
                         assert bool(ref.ref_traj5_check_max_acc_rate(h, lim)) == bool(rates[b, 1] < lim)
             finally:
                 ref.ref_traj5_destroy(h)
-    # S = 4 (septic pieces; no reference class is instantiated for it here): dense sampling only
-    pb4 = synth.make_problems(32, N=6, K=16, S=4)
+    # S = 4 (septic pieces): dense sampling, and the reference's Trajectory<7> -- which also takes the device's
+    # coefficients through emplace_back and returns the waypoints and the snap energy (up to the reference's own
+    # m_34 typo, trajectory.hpp:385: 2 getTrajCost(4) = E - sum 80 T^2 c5.c4, tests/test_oracle_minco.py)
+    B4, N4 = 32, 6
+    pb4 = synth.make_problems(B4, N=N4, K=16, S=4)
     mb4 = handles[4]
     mb4.set_params(default_params(4))
     mb4.set_problems(pb4)
     r4 = mb4.optimize(pb4.x0())
     rt4 = mb4.max_rates(r4["coeffs"], r4["T"])
-    for b in range(0, 32, 7):
+    for b in range(0, B4, 7):
         np.testing.assert_allclose(rt4[b], _dense_rates(r4["coeffs"][b], r4["T"][b]), rtol=1e-7)
+    if ref is not None and hasattr(ref, "ref_traj7_create"):
+        dp = C.POINTER(C.c_double)
+        ref.ref_traj7_create.restype = C.c_void_p; ref.ref_traj7_create.argtypes = [C.c_int, dp, dp]
+        ref.ref_traj7_destroy.argtypes = [C.c_void_p]
+        ref.ref_traj7_cost.restype = C.c_double; ref.ref_traj7_cost.argtypes = [C.c_void_p, C.c_int]
+        ref.ref_traj7_positions.argtypes = [C.c_void_p, dp]
+        for fn in (ref.ref_traj7_max_vel_rate, ref.ref_traj7_max_acc_rate):
+            fn.restype = C.c_double; fn.argtypes = [C.c_void_p]
+        q4 = r4["x"][:, N4:].reshape(B4, N4 - 1, 3)
+        fw4 = mb4.minco_forward(pb4.head, pb4.tail, q4, r4["T"])
+        for b in range(B4):
+            c = np.ascontiguousarray(r4["coeffs"][b]); T = np.ascontiguousarray(r4["T"][b])   # [N][3][8] descending
+            h = ref.ref_traj7_create(N4, T.ctypes.data_as(dp), c.ctypes.data_as(dp))
+            try:
+                assert abs(ref.ref_traj7_max_vel_rate(h) - rt4[b, 0]) <= 1e-7 * rt4[b, 0]
+                assert abs(ref.ref_traj7_max_acc_rate(h) - rt4[b, 1]) <= 1e-7 * rt4[b, 1]
+                P = np.zeros((N4 + 1, 3)); ref.ref_traj7_positions(h, P.ctypes.data_as(dp))
+                np.testing.assert_allclose(P[0], pb4.head[b, 0], atol=1e-9)
+                np.testing.assert_allclose(P[1:N4], q4[b], atol=1e-6)
+                np.testing.assert_allclose(P[N4], pb4.tail[b, 0], atol=1e-5)
+                quirk = sum(80.0 * T[i] ** 2 * float((c[i, :, 2] * c[i, :, 3]).sum()) for i in range(N4))   # c5 = k 2, c4 = k 3
+                E = fw4["energy"][b]
+                assert abs(2.0 * ref.ref_traj7_cost(h, 4) + quirk - E) <= 1e-7 * abs(E)
+            finally:
+                ref.ref_traj7_destroy(h)
 
 
 def test_shape_and_state_validation():

@@ -407,3 +407,49 @@ def test_torch_reference_equals_oracle(oracle, S, N):
     assert np.abs(grads[0].numpy() - gT).max() <= 10 * tol * np.abs(gT).max()
     if N > 1:
         assert np.abs(grads[1].numpy() - gq).max() <= 10 * tol * np.abs(gq).max()
+
+
+def test_output_contract_s4_against_reference_trajectory7(oracle):
+    """MINCO_S4NU (septic pieces) into the reference's Trajectory<7> (trajectory.hpp compiled verbatim): positions and
+    derivative evaluation as for S = 3, and the snap energy.  trajectory.hpp:385 carries the reference's known typo
+    (m_34 = 1400 where the integral gives 1440), so 2 * getTrajCost(4) misses the true
+    int |p''''|^2 by exactly sum over pieces and axes of 80 T^2 c5 c4 -- which pins layout AND documents the quirk."""
+    import ctypes as C
+    ref = oracle.ref
+    if ref is None or not hasattr(ref, "ref_traj7_create"):
+        pytest.skip("oracle/_ref (Trajectory<7>) not built")
+    dp = C.POINTER(C.c_double)
+    ref.ref_traj7_create.restype = C.c_void_p; ref.ref_traj7_create.argtypes = [C.c_int, dp, dp]
+    ref.ref_traj7_destroy.argtypes = [C.c_void_p]
+    ref.ref_traj7_cost.restype = C.c_double; ref.ref_traj7_cost.argtypes = [C.c_void_p, C.c_int]
+    ref.ref_traj7_eval.argtypes = [C.c_void_p, C.c_double, dp, dp, dp, dp]
+    ref.ref_traj7_positions.argtypes = [C.c_void_p, dp]
+    rng = np.random.default_rng(12)
+    for N in (1, 3, 6):
+        head = rng.normal(size=(4, 3)); tail = rng.normal(size=(4, 3))
+        q = np.cumsum(rng.normal(size=(max(N - 1, 1), 3)), axis=0)[: N - 1]
+        T = rng.uniform(0.6, 2.0, size=N)
+        out = oracle.minco_forward(4, head, tail, q, T)
+        flat = np.ascontiguousarray(out["flat"]); Tc = np.ascontiguousarray(T)     # [N][3][8], k = 0 highest power
+        h = ref.ref_traj7_create(N, Tc.ctypes.data_as(dp), flat.ctypes.data_as(dp))
+        try:
+            c = out["coeffs"].reshape(N, 8, 3)                                    # ascending powers
+            quirk = sum(80.0 * T[i] ** 2 * float((c[i, 5] * c[i, 4]).sum()) for i in range(N))
+            assert abs(2.0 * ref.ref_traj7_cost(h, 4) + quirk - out["energy"]) <= 1e-10 * abs(out["energy"])
+            assert abs(quirk) > 1e-9 * abs(out["energy"])                          # the typo is really there
+            P = np.zeros((N + 1, 3)); ref.ref_traj7_positions(h, P.ctypes.data_as(dp))
+            np.testing.assert_allclose(P[0], head[0], atol=1e-12)
+            np.testing.assert_allclose(P[1:N], q, atol=1e-8)
+            np.testing.assert_allclose(P[N], tail[0], atol=1e-7)
+            t0 = np.concatenate([[0.0], np.cumsum(T)])
+            for t in rng.uniform(0.0, T.sum(), size=8):
+                i = min(int(np.searchsorted(t0, t, side="left")) - 1, N - 1); i = max(i, 0)
+                s_ = t - t0[i]
+                got = [np.zeros(3) for _ in range(4)]
+                ref.ref_traj7_eval(h, t, *[g.ctypes.data_as(dp) for g in got])
+                for d, g in enumerate(got):
+                    fac = np.array([np.prod([k - u for u in range(d)]) if k >= d else 0.0 for k in range(8)])
+                    want = (c[i] * (fac * s_ ** np.maximum(np.arange(8) - d, 0))[:, None]).sum(axis=0)
+                    np.testing.assert_allclose(g, want, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(want).max()))
+        finally:
+            ref.ref_traj7_destroy(h)
