@@ -176,8 +176,12 @@ static int do_evaluate(mincob_ctx *h, const BatchArgs &a) {
 static int do_optimize(mincob_ctx *h, BatchArgs &a) {
     const LaunchTable *t = table_for(h->prm.S, a.N);
     const size_t need = t->optimize_scratch(h->sm_count, h->dp, a);
+    const void *before = h->b_hist.p;
     int rc = ensure(h, h->b_hist, need);
     if (rc) return rc;
+    // The two-loop recursion reads history slots a problem has not written yet (their contribution is predicated
+    // off): give a fresh slab defined contents once, so those reads never see arbitrary bit patterns.
+    if (h->b_hist.p != before) CU(h, cudaMemsetAsync(h->b_hist.p, 0, h->b_hist.cap, h->stream));
     a.hist = (double *)h->b_hist.p;
     return launched(h, table_for(h->prm.S, a.N)->optimize(h->stream, h->sm_count, h->dp, a), "optimize_kernel");
 }
