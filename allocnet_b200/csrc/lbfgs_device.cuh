@@ -303,10 +303,14 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #endif
 
         // ---- reductions every group may need ------------------------------------------------------
-        const double gn = ginf<LPT>(FULL, g), xn = ginf<LPT>(FULL, x);
+        // |g|_inf and |x|_inf only feed the g_epsilon test (lbfgs.hpp:531, :600), which can never fire for g_epsilon = 0
+        // (the default here and upstream): a warp-uniform branch then skips both reductions
+        double gn = 1.0, xn = 1.0;
+        if (P.g_eps > 0.0) { gn = ginf<LPT>(FULL, g); xn = ginf<LPT>(FULL, x); }
         const double gg = gdot<LPT>(FULL, g, g);
         const double gd = gdot<LPT>(FULL, g, d);
-        const double pfk = (past > 0) ? pf[k % past] : 0.0;
+        const int kslot = (past > 0) ? k % past : 0;   // slot of the `past` ring this iteration reads, then overwrites
+        const double pfk = (past > 0) ? pf[kslot] : 0.0;
         __syncwarp();
 
         // ---- per-group scalar decisions (no shuffles below until the next section) -------------
@@ -320,10 +324,10 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             k = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] = -g[i];
-            if (gn / fmax(1.0, xn) < P.g_eps) {
+            if (gn < P.g_eps * fmax(1.0, xn)) {   // gnorm / max(1, xnorm) < g_epsilon (lbfgs.hpp:531), without the fp64 division
                 ret = LBFGS_CONVERGENCE; finish = 1;
             } else {
-                stp = 1.0 / sqrt(gg);
+                stp = rsqrt(gg);                // 1 / |g| (lbfgs.hpp:543), one rounding instead of two
                 k = 1; end = 0; bound = 0;
                 start_ls = true;
             }
@@ -362,10 +366,11 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 for (int i = 0; i < 4; ++i) { x[i] = xp[i]; g[i] = gp[i]; }
                 ret = fail; finish = 1;
             } else if (done) {              // lbfgs.hpp:580-640
-                if (gn / fmax(1.0, xn) < P.g_eps) { ret = LBFGS_CONVERGENCE; finish = 1; }
+                if (gn < P.g_eps * fmax(1.0, xn)) { ret = LBFGS_CONVERGENCE; finish = 1; }
                 if (!finish && past > 0) {
-                    if (past <= k && fabs(pfk - fx) / fmax(1.0, fabs(fx)) < P.delta) { ret = LBFGS_STOP; finish = 1; }
-                    if (!finish) { write_pf = true; pf_slot = k % past; }
+                    // |pf - fx| / max(1, |fx|) < delta (lbfgs.hpp:610-614) as a product: an fp64 division is ~35 instructions
+                    if (past <= k && fabs(pfk - fx) < P.delta * fmax(1.0, fabs(fx))) { ret = LBFGS_STOP; finish = 1; }
+                    if (!finish) { write_pf = true; pf_slot = kslot; }
                 }
                 if (!finish && P.max_iter != 0 && P.max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; finish = 1; }
                 if (!finish) upd = true;
@@ -380,6 +385,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             for (int i = 0; i < 4; ++i) { sv[i] = x[i] - xp[i]; yv[i] = g[i] - gp[i]; }
             const double ys = gdot<LPT>(FULL, yv, sv), yy = gdot<LPT>(FULL, yv, yv);
             const double ss = gdot<LPT>(FULL, sv, sv), gpgp = gdot<LPT>(FULL, gp, gp);
+            const double iys = 1.0 / ys;   // the two-loop recursion only ever divides by y.s
             bool two = false;
             if (upd) {
                 ++k;
@@ -388,8 +394,9 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 slot[1] = make_double4(yv[0], yv[1], yv[2], yv[3]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) d[i] = -g[i];
-                if (lig == 0) ysv[end] = 1.0 / ys;   // the two-loop recursion only ever divides by y.s
-                two = ys > ss * sqrt(gpgp) * P.cautious;
+                if (lig == 0) ysv[end] = iys;
+                // ys > cautious * ss * |gp| (lbfgs.hpp:655), squared so that no fp64 square root is needed (the right side is >= 0)
+                two = ys > 0.0 && ys * ys > (ss * P.cautious) * (ss * P.cautious) * gpgp;
                 if (two) {
                     ++bound;
                     bound = m < bound ? m : bound;
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 constexpr int HKEEP = MEM - HDEP > 1 ? MEM - HDEP : 1;
                 hq[0].s = make_double4(sv[0], sv[1], sv[2], sv[3]);
                 hq[0].y = make_double4(yv[0], yv[1], yv[2], yv[3]);
-                hq[0].rys = 1.0 / ys;
+                hq[0].rys = iys;
                 double al[MEM > 0 ? MEM : 1];
                 // backward pass, newest pair first (lbfgs.hpp:676-687)
 #pragma unroll
