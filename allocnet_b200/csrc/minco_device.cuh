@@ -271,14 +271,12 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
     for (int a = 0; a < b; ++a)
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
+            // hd is zero on every lane but 0 and td on every lane but N-1 (all callers pass them so): no predicate needed
             double ev = wb[a] * dP[x], fv = wa[a] * dP[x];
-            if (lig == 0) {
 #pragma unroll
-                for (int c = 0; c < b; ++c) ev += Bm[c][a] * hd[c][x];
-            }
-            if (lig == N - 1) {
-#pragma unroll
-                for (int c = 0; c < b; ++c) fv += Bm[a][c] * td[c][x];
+            for (int c = 0; c < b; ++c) {
+                ev = fma(Bm[c][a], hd[c][x], ev);
+                fv = fma(Bm[a][c], td[c][x], fv);
             }
             e[a][x] = ev; f[a][x] = fv;
         }
@@ -409,8 +407,8 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
             const double yn = sh_dn<LPT>(mask, y[a][x], 1);
             const double ys = (lig == 0) ? hd[a][x] : y[a][x];
             const double ye = (lig == N - 1) ? td[a][x] : yn;
-            sh[1 + a][x] = active ? lam[a + 1] * ys : 0.0;
-            sh[S + 1 + a][x] = active ? lam[a + 1] * ye : 0.0;
+            sh[1 + a][x] = lam[a + 1] * ys;       // lanes >= N: identity rows with zero right-hand sides gave y = 0
+            sh[S + 1 + a][x] = lam[a + 1] * ye;
         }
     // Hermite -> monomial.  Hhat[k][0] == -Hhat[k][S] for k >= S: positions enter only through dP.
     double ip = 1.0;  // iT^k
@@ -424,7 +422,7 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
             } else {
                 v = HK::H(k, S) * dP[x];
 #pragma unroll
-                for (int d = 1; d < S; ++d) v += HK::H(k, d) * sh[d][x] + HK::H(k, S + d) * sh[S + d][x];
+                for (int d = 1; d < S; ++d) v = fma(HK::H(k, S + d), sh[S + d][x], fma(HK::H(k, d), sh[d][x], v));
             }
             chat[k][x] = v;
             sp.c[k][x] = v * ip;
@@ -461,10 +459,10 @@ __device__ __forceinline__ void energy_partials(const Spline<S, LPT, ST> &sp, co
             }
             e += chat[a][x] * qc;
             et += chat[a][x] * qt;
-            G[a][x] = active ? 2.0 * sp.t5 * tp[a] * qc : 0.0;
+            G[a][x] = 2.0 * sp.t5 * tp[a] * qc;   // lanes >= N hold zero coefficients (spline_solve): every term is 0 there
         }
-    energy = active ? sp.t5 * e : 0.0;
-    gT = active ? sp.t5 * sp.iT * et : 0.0;
+    energy = sp.t5 * e;
+    gT = sp.t5 * sp.iT * et;
 }
 
 // One half-plane row (nx,ny,nz,d); rows are 32-byte aligned.  PSMEM = true: the row sits in the
@@ -685,7 +683,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
 #pragma unroll
         for (int k = 0; k < D; ++k) {
 #pragma unroll
-            for (int x = 0; x < 3; ++x) chat[k][x] = active ? sp.c[k][x] * tk : 0.0;
+            for (int x = 0; x < 3; ++x) chat[k][x] = sp.c[k][x] * tk;   // zero on lanes >= N, like G and hence z
             tk *= sp.T;
         }
 #pragma unroll
@@ -704,14 +702,14 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
     double r[b][3], gp[3];
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
-        const double pe = sh_up<LPT>(mask, active ? z[S][x] : 0.0, 1);
+        const double pe = sh_up<LPT>(mask, z[S][x], 1);
         gp[x] = junction ? pe + z[0][x] : 0.0;
     }
 #pragma unroll
     for (int a = 0; a < b; ++a)
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
-            const double ee = sh_up<LPT>(mask, active ? lam[a + 1] * z[S + 1 + a][x] : 0.0, 1);
+            const double ee = sh_up<LPT>(mask, lam[a + 1] * z[S + 1 + a][x], 1);
             r[a][x] = junction ? ee + lam[a + 1] * z[1 + a][x] : 0.0;
         }
     sweep_apply<S, LPT, ST>(mask, rounds, mul, r);  // r <- mu_lig
@@ -724,7 +722,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
             const double mn = sh_dn<LPT>(mask, r[a][x], 1);
-            lm[1 + a][x] = junction ? lam[a + 1] * r[a][x] : 0.0;
+            lm[1 + a][x] = lam[a + 1] * r[a][x];   // r = 0 off the junctions (identity rows)
             lm[S + 1 + a][x] = (lig < N - 1) ? lam[a + 1] * mn : 0.0;
         }
     // wm = What (L m), ws = What (L s)  (positions through dP: What[:,0] == -What[:,S])
@@ -738,24 +736,25 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
             double vm = 0.0, vs = HK::W(a, S) * sh[S][x];
 #pragma unroll
             for (int d = 1; d < S; ++d) {
-                vm += HK::W(a, d) * lm[d][x] + HK::W(a, S + d) * lm[S + d][x];
-                vs += HK::W(a, d) * sh[d][x] + HK::W(a, S + d) * sh[S + d][x];
+                vm = fma(HK::W(a, S + d), lm[S + d][x], fma(HK::W(a, d), lm[d][x], vm));
+                vs = fma(HK::W(a, S + d), sh[S + d][x], fma(HK::W(a, d), sh[d][x], vs));
             }
             wm[a] = vm; ws[a] = vs;
         }
         wm0[x] = wm[0]; wmS[x] = wm[S];
 #pragma unroll
         for (int d = 1; d < S; ++d) {
-            acc_ms += lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d];
-            acc_dms += (double)d * (lm[d][x] * ws[d] + lm[S + d][x] * ws[S + d]);
-            acc_dsm += (double)d * (sh[d][x] * wm[d] + sh[S + d][x] * wm[S + d]);
-            zds += (double)d * (z[d][x] * sh[d][x] + z[S + d][x] * sh[S + d][x]);
+            const double lw = fma(lm[S + d][x], ws[S + d], lm[d][x] * ws[d]);
+            acc_ms += lw;
+            acc_dms = fma((double)d, lw, acc_dms);
+            acc_dsm = fma((double)d, fma(sh[S + d][x], wm[S + d], sh[d][x] * wm[d]), acc_dsm);
+            zds = fma((double)d, fma(z[S + d][x], sh[S + d][x], z[d][x] * sh[d][x]), zds);
         }
     }
     // dJ/dq_j = g_p[j] - t5_j wm_j[0] - (t5 wm[S])_{j-1}
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
-        const double prev = sh_up<LPT>(mask, active ? sp.t5 * wmS[x] : 0.0, 1);
+        const double prev = sh_up<LPT>(mask, sp.t5 * wmS[x], 1);
         gq[x] = junction ? gp[x] - sp.t5 * wm0[x] - prev : 0.0;
     }
     // dJ/dT_i = partial - (1/T) sum k G_k.c_k + z.(L' s) - m^T W' s ;  L' = (d/T) L
