@@ -34,6 +34,7 @@ SYMBOLS = [
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
     "mincob_max_rates", "mincob_max_rates_device", "mincob_minco_forward_device", "mincob_minco_propagate_device",
+    "mincob_optimize_sharded_local", "mincob_gathered_device",
 ]
 
 
@@ -76,6 +77,8 @@ def load_library() -> C.CDLL:
     L.mincob_allgather_device.argtypes = [_vp, _vp, _vp, C.c_int64]
     L.mincob_comm_destroy.argtypes = [_vp]
     L.mincob_optimize_sharded.argtypes = [_vp] + [_vp] * 7
+    L.mincob_optimize_sharded_local.argtypes = [_vp] + [_vp] * 7
+    L.mincob_gathered_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]
     L.mincob_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
     L.mincob_host_free.argtypes = [_vp]
     L.mincob_check_feasibility.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
@@ -285,6 +288,18 @@ class MincoBatch:
     def allgather_device(self, send, recv, count_per_rank: int):
         self._check(self.L.mincob_allgather_device(self.h, _dev_ptr(send), _dev_ptr(recv), int(count_per_rank)))
 
+
+    def optimize_sharded_local_host_buffers(self, x, f, status, iters, evals, coeffs_local, T):
+        """Sharded job on a rank that does not consume the gathered coefficients: same collective, only this rank's own
+        results come back to the host (mincob_optimize_sharded_local)."""
+        self._check(self.L.mincob_optimize_sharded_local(self.h, _np_ptr(x), _np_ptr(f), _np_ptr(status), _np_ptr(iters),
+                                                         _np_ptr(evals), _np_ptr(coeffs_local), _np_ptr(T)))
+
+    def gathered_device(self):
+        """(device pointer, count of doubles) of the coefficients gathered by the last sharded optimize call."""
+        p = _vp(); n = C.c_int64(0)
+        self._check(self.L.mincob_gathered_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
 
     def optimize_sharded_host_buffers(self, x, f, status, iters, evals, coeffs_all, T):
         """Config 5 on caller-owned host arrays: optimize this rank's shard, all-gather the coefficients."""

@@ -88,6 +88,7 @@ struct mincob_ctx {
     unsigned long long *total_evals = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    int64_t gathered_count = 0;   // doubles in b_gather after the last sharded optimize call
     std::string err;
 };
 
@@ -713,13 +714,15 @@ int mincob_allgather_device(mincob_handle h, const double *send, double *recv, i
     return 0;
 }
 
-int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
-                            double *coeffs_all, double *T) {
+// gather_to_host: coeffs is [nranks*B][N][3][2S] and receives every rank's coefficients; otherwise coeffs is this
+// rank's own [B][N][3][2S] and the gathered array stays on the device (mincob_gathered_device).
+static int optimize_sharded(mincob_ctx *h, bool gather_to_host, double *x, double *f, int32_t *status, int32_t *iters,
+                            int32_t *evals, double *coeffs, double *T) {
     if (!h) return MINCOB_E_INVALID;
-    if (!h->comm || h->nranks == 1) return mincob_optimize(h, x, f, status, iters, evals, coeffs_all, T);
+    if (!h->comm || h->nranks == 1) return mincob_optimize(h, x, f, status, iters, evals, coeffs, T);
     int rc = have_problems(h);
     if (rc) return rc;
-    if (!x || !coeffs_all) return fail(h, MINCOB_E_INVALID, "x and coeffs_all must be non-null");
+    if (!x || (gather_to_host && !coeffs)) return fail(h, MINCOB_E_INVALID, "x and coeffs_all must be non-null");
     CU(h, cudaSetDevice(h->device));
     const size_t B = h->B, N = h->N, n = N + 3 * (N - 1), S = h->prm.S;
     const size_t nx = B * n * 8, nf = B * 8, ni = B * 4, cnt = B * N * 3 * 2 * S, nc = cnt * 8, nt = B * N * 8;
@@ -736,14 +739,34 @@ int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *stat
     if (rc) return rc;
     const bool ran = h->timed;
     if ((rc = mincob_allgather_device(h, (const double *)h->b_coeffs.p, (double *)h->b_gather.p, (int64_t)cnt))) return rc;
+    h->gathered_count = (int64_t)cnt * h->nranks;
     if (ran) CU(h, cudaMemcpyAsync(x, h->b_x.p, nx, cudaMemcpyDeviceToHost, h->stream));
     if (f && ran) CU(h, cudaMemcpyAsync(f, h->b_f.p, nf, cudaMemcpyDeviceToHost, h->stream));
     if (status) CU(h, cudaMemcpyAsync(status, h->b_status.p, ni, cudaMemcpyDeviceToHost, h->stream));
     if (iters && ran) CU(h, cudaMemcpyAsync(iters, h->b_iters.p, ni, cudaMemcpyDeviceToHost, h->stream));
     if (evals && ran) CU(h, cudaMemcpyAsync(evals, h->b_evals.p, ni, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaMemcpyAsync(coeffs_all, h->b_gather.p, nc * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    if (gather_to_host) CU(h, cudaMemcpyAsync(coeffs, h->b_gather.p, nc * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    else if (coeffs) CU(h, cudaMemcpyAsync(coeffs, h->b_coeffs.p, nc, cudaMemcpyDeviceToHost, h->stream));
     if (T && ran) CU(h, cudaMemcpyAsync(T, h->b_T.p, nt, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
+                            double *coeffs_all, double *T) {
+    return optimize_sharded(h, true, x, f, status, iters, evals, coeffs_all, T);
+}
+
+int mincob_optimize_sharded_local(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
+                                  double *coeffs_local, double *T) {
+    return optimize_sharded(h, false, x, f, status, iters, evals, coeffs_local, T);
+}
+
+int mincob_gathered_device(mincob_handle h, const double **coeffs_all_d, int64_t *count) {
+    if (!h || !coeffs_all_d) return MINCOB_E_INVALID;
+    if (!h->b_gather.p || h->gathered_count <= 0) return fail(h, MINCOB_E_STATE, "no sharded optimize call has gathered coefficients yet");
+    *coeffs_all_d = (const double *)h->b_gather.p;
+    if (count) *count = h->gathered_count;
     return 0;
 }
 

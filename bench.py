@@ -292,7 +292,9 @@ def main():
         h_x0, h_x = pin((B, n)), pin((B, n))
         h_f, h_T = pin((B,)), pin((B, N))
         h_status, h_iters, h_evals = pin((B,), np.int32), pin((B,), np.int32), pin((B,), np.int32)
-        h_call = pin((world * cnt,))
+        # rank 0 is the consumer of the whole job: it reads back the coefficients of every rank (rank-major); the other
+        # ranks take part in the same all-gather and read back their own shard only
+        h_call = pin((world * cnt,)) if rank == 0 else pin((cnt,))
         h_head[...] = pb.head; h_tail[...] = pb.tail; h_x0[...] = pb.x0()
         if K > 0:
             h_hp[...] = pb.hpolys; h_hr[...] = pb.hrows
@@ -305,7 +307,10 @@ def main():
         def e2e_step():
             h_x[...] = h_x0
             mb.set_problems(hpb)                                       # H2D: head, tail, hpolys, hrows
-            mb.optimize_sharded_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)  # H2D x; D2H results
+            if rank == 0:
+                mb.optimize_sharded_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)   # H2D x; D2H results
+            else:
+                mb.optimize_sharded_local_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)
         for _ in range(2):
             e2e_step()
         fence()
@@ -320,7 +325,9 @@ def main():
         d2h = B * n * 8 + B * 8 + 3 * B * 4 + world * cnt * 8 + B * N * 8
         e2e = {"value": world * B * a.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / a.steps,
-               "api": "mincob_set_problems + mincob_optimize_sharded (host pointers, pinned)",
+               "api": "mincob_set_problems + mincob_optimize_sharded (host pointers, pinned)" +
+                      ("; rank 0 reads back all ranks' coefficients (d2h_bytes_per_step is rank 0's), the other ranks "
+                       "(mincob_optimize_sharded_local) their own shard" if world > 1 else ""),
                "ok_fraction": float((h_status >= 0).mean())}
         mb.set_problems_device(B, N, K, d_head, d_tail, d_hp, d_hr)
 

@@ -174,6 +174,13 @@ int mincob_comm_destroy(mincob_handle h);
  *      it is mincob_optimize.  Every rank must call it with the same B. */
 int mincob_optimize_sharded(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters,
                             int32_t *evals, double *coeffs_all, double *T);
+/*      Same job and same collective, but only this rank's own coefficients [B][N][3][2S] are copied to the host
+ *      (coeffs_local may be NULL); the gathered array of all ranks stays in device memory, where
+ *      mincob_gathered_device returns it ([nranks*B][N][3][2S], rank-major; valid until the next sharded call).
+ *      A job in which one rank consumes everything calls mincob_optimize_sharded there and this on the others. */
+int mincob_optimize_sharded_local(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters,
+                                  int32_t *evals, double *coeffs_local, double *T);
+int mincob_gathered_device(mincob_handle h, const double **coeffs_all_d, int64_t *count);
 
 /* ---- pinned host memory for the host-pointer entry points (cudaHostAlloc / cudaFreeHost), so a
  *      C++ caller such as LearningPlanner needs no CUDA headers of its own. */
