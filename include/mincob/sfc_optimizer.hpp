@@ -176,6 +176,15 @@ public:
     void optimize(double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals, double *coeffs, double *T) {
         check(h, mincob_optimize(h, x, f, status, iters, evals, coeffs, T), "optimize");
     }
+    // what Trajectory<D>::getMaxVelRate / getMaxAccRate (gcopter/trajectory.hpp:598-622) return, per trajectory, plus the
+    // same for jerk: rates [B][3]; checkMaxVelRate(v) / checkMaxAccRate(a) are rates[b][0] < v / rates[b][1] < a
+    void maxRates(const double *coeffs, const double *T, double *rates) {
+        check(h, mincob_max_rates(h, coeffs, T, rates), "maxRates");
+    }
+    // sampled max |v|, |a|, |j| and the largest corridor residual (<= 0: inside): report [B][4]
+    void checkFeasibility(const double *coeffs, const double *T, int samples, double *report) {
+        check(h, mincob_check_feasibility(h, coeffs, T, samples, report), "checkFeasibility");
+    }
     mincob_handle handle() const { return h; }
 
 private:
