@@ -376,8 +376,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": f"optimize_kernel<S={S}>", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
-                         "note": "algorithmic bytes = sum(evals)*bytes_eval + B*coeff bytes (SURVEY 8d); the kernel is "
-                                 "fp64-pipe bound, half-planes are re-read from L1/L2 not HBM"},
+                         "note": "algorithmic bytes = sum(evals)*bytes_eval + B*coeff bytes (SURVEY 8d); the persistent kernel keeps "
+                                 "a problem on chip for its ~420 evaluations, so DRAM traffic is ~230x lower; what bounds it is "
+                                 "fp64 latency and instruction supply (roofline_fp64, profiles/)"},
             "gpu_launches": a.steps,
             "clocks": clk,
         }
