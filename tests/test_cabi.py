@@ -66,3 +66,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "minco_oracle.hpp" not in txt, f
+
+
+def test_null_and_state_errors_without_a_device(lib):
+    """Entry points that take a handle refuse NULL handles with MINCOB_E_INVALID before touching CUDA (what a binding in
+    another language sees first), and the error strings are stable."""
+    import ctypes as C
+    E_INVALID = lib.mincob_evaluate(None, None, None, None)
+    assert E_INVALID != 0
+    assert lib.mincob_optimize(None, None, None, None, None, None, None, None) == E_INVALID
+    assert lib.mincob_max_rates(None, None, None, None) == E_INVALID
+    assert lib.mincob_check_feasibility(None, None, None, 8, None) == E_INVALID
+    assert lib.mincob_optimize_sharded(None, None, None, None, None, None, None, None) == E_INVALID
+    assert lib.mincob_optimize_sharded_local(None, None, None, None, None, None, None, None) == E_INVALID
+    p = C.c_void_p(); n = C.c_int64(0)
+    assert lib.mincob_gathered_device(None, C.byref(p), C.byref(n)) == E_INVALID
+    v = C.c_double(0.0)
+    assert lib.mincob_measure_fp64_peak(None, C.byref(v)) == E_INVALID
+    assert b"invalid" in lib.mincob_strerror(E_INVALID).lower()

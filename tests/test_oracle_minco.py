@@ -453,3 +453,34 @@ def test_output_contract_s4_against_reference_trajectory7(oracle):
                     np.testing.assert_allclose(g, want, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(want).max()))
         finally:
             ref.ref_traj7_destroy(h)
+
+
+def test_reference_max_rates_septic_against_dense_sampling(oracle):
+    """Same pin for the reference's Trajectory<7> (MINCO_S4NU): getMaxVelRate / getMaxAccRate through root_finder.hpp
+    (degree-12 / degree-10 rate polynomials, Sturm isolation) equal a dense sampling."""
+    import ctypes as C
+    ref = oracle.ref
+    if ref is None or not hasattr(ref, "ref_traj7_max_vel_rate"):
+        pytest.skip("oracle/_ref (Trajectory<7>) not present")
+    dp = C.POINTER(C.c_double)
+    ref.ref_traj7_create.restype = C.c_void_p; ref.ref_traj7_create.argtypes = [C.c_int, dp, dp]
+    ref.ref_traj7_destroy.argtypes = [C.c_void_p]
+    for fn in (ref.ref_traj7_max_vel_rate, ref.ref_traj7_max_acc_rate):
+        fn.restype = C.c_double; fn.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(21)
+    for N in (1, 4):
+        head, tail, q, T = rand_problem(rng, 4, N)
+        out = oracle.minco_forward(4, head, tail, q, T)
+        flat = np.ascontiguousarray(out["flat"]); Tc = np.ascontiguousarray(T)
+        want = np.zeros(2)
+        for i in range(N):
+            t = np.linspace(0.0, T[i], 40001)
+            for d in (1, 2):
+                v = np.stack([np.polyval(np.polyder(flat[i, a], d), t) for a in range(3)])
+                want[d - 1] = max(want[d - 1], np.sqrt((v * v).sum(axis=0).max()))
+        h = ref.ref_traj7_create(N, Tc.ctypes.data_as(dp), flat.ctypes.data_as(dp))
+        try:
+            assert abs(ref.ref_traj7_max_vel_rate(h) - want[0]) <= 1e-7 * want[0]
+            assert abs(ref.ref_traj7_max_acc_rate(h) - want[1]) <= 1e-7 * want[1]
+        finally:
+            ref.ref_traj7_destroy(h)
