@@ -570,3 +570,24 @@ def test_config4_pipeline_net_warm_start_on_device(handles, oracle):
     assert np.median(rel) <= 2e-3 and np.mean(rel < 2e-2) >= 0.85, (np.median(rel), rel.max())
     assert abs(res["evals"].mean() / ref["evals"].mean() - 1.0) <= 0.15
     mb.set_params(default_params(3))
+
+
+def test_gradient_norm_stop(handles, oracle):
+    """g_epsilon > 0 with the `past` test switched off: every problem must end with LBFGS_CONVERGENCE (0), the code of
+    lbfgs.hpp:531 / :600, and at the returned x the ORACLE's gradient satisfies |g|_inf / max(1, |x|_inf) < g_epsilon
+    -- the device evaluates that test as a product and skips its two reductions altogether when g_epsilon = 0."""
+    B, N = 64, 5
+    prm = energy_only(default_params(3, g_epsilon=1e-2, past=0, max_iterations=2000))
+    pb = synth.make_problems(B, N=N, K=0, S=3)
+    mb = handles[3]
+    mb.set_params(prm)
+    mb.set_problems(pb)
+    res = mb.optimize(pb.x0())
+    ref = oracle.optimize_batch(prm, pb, nthreads=8)
+    assert (res["status"] == P.LBFGS_CONVERGENCE).all(), np.unique(res["status"], return_counts=True)
+    assert (ref["status"] == P.LBFGS_CONVERGENCE).all()
+    _, go = oracle.cost_batch(prm, pb, res["x"], nthreads=8)
+    crit = np.abs(go).max(axis=1) / np.maximum(1.0, np.abs(res["x"]).max(axis=1))
+    assert (crit < 1e-2 * (1.0 + 1e-6)).all(), float(crit.max())
+    assert abs(res["iters"].mean() / ref["iters"].mean() - 1.0) <= 0.25
+    mb.set_params(default_params(3))
