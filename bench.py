@@ -282,6 +282,23 @@ def main():
                "corridor_within_2cm": float((rep[:, 3] <= 0.02).mean()) if K > 0 else None,
                "max_speed_p99": float(np.percentile(rep[:, 0], 99))}
 
+    # ---- the per-evaluation kernel on its own (the lbfgs_evaluate_t body for the whole batch, one launch): this is the
+    #      launch BASELINE.json's "one fused kernel per L-BFGS evaluation" describes, with its algorithmic HBM bytes -------
+    evk = None
+    if rank == 0:
+        d_g = torch.empty_like(d_x0)
+        for _ in range(3):
+            mb.evaluate_device(d_x0, d_f, d_g)
+        torch.cuda.synchronize(dev)
+        ev_ms = []
+        for _ in range(10):
+            mb.evaluate_device(d_x0, d_f, d_g)
+            ev_ms.append(mb.last_kernel_ms()[0])          # CUDA events around the launch, on its stream; synchronises
+        ev = float(np.median(ev_ms))
+        ev_bytes = B * bytes_eval(N, K, S)
+        evk = {"kernel": f"evaluate_kernel<S={S}>", "ms_per_launch": ev, "evals_per_s": B / (ev * 1e-3),
+               "algorithmic_bytes_per_launch": int(ev_bytes), "achieved_gbs": ev_bytes / (ev * 1e-3) / 1e9}
+
     # ---- e2e leg: host pointers through the C-ABI, copies inside the timed region -------------
     e2e = None
     if not a.no_e2e:
@@ -384,6 +401,9 @@ def main():
         }
         if fp64 is not None:
             line["roofline_fp64"] = fp64
+        if evk is not None:
+            evk["frac_of_hbm_peak"] = evk["achieved_gbs"] / peak
+            line["evaluate_kernel"] = evk
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not a.no_cpu:
