@@ -65,6 +65,35 @@ def test_minco_forward_and_propagate(handles, oracle, S, N):
         assert np.abs(gT[b] - gT_ref).max() <= ptol * np.abs(gT_ref).max()
 
 
+@pytest.mark.parametrize("name", ["n2", "n3", "n5", "n8"])
+def test_device_minco_against_reference_qp_matrices(handles, name):
+    """The DEVICE's MINCO_S3NU (setParameters, getEnergy, partial gradients, propogateGrad) against matrices built
+    by the reference's own code (tests/golden/ref_qp_*.npz: Q, A, b and autograd Jacobians dQ/dT, dA/dT of
+    network/utils/min_traj_opt.py::fill_eq_obj, the twin of planner/qp_solver.hpp:148-242) -- no oracle involved:
+    coefficients == KKT minimiser (1e-9), A z == b, E == z^T Q z, dE/dc == 2 Q z, dE/dT == z^T dQ z, and the total
+    gradients == KKT sensitivities (2e-9)."""
+    from ref_qp_util import load_ref_qp, ref_qp_problem, ref_qp_kkt
+    c = load_ref_qp(name)
+    head, tail, q, T = ref_qp_problem(c, 8)
+    N = len(T)
+    z, lam_a, lam_w = ref_qp_kkt(c, q)
+    out = handles[3].minco_forward(head[None], tail[None], q[None], T[None])
+    zd = out["flat"][0].reshape(-1)
+    Q, A, b, dQ, dA = c["Q"], c["A"], c["b"], c["dQ"], c["dA"]
+    np.testing.assert_allclose(zd, z, rtol=0, atol=TOL * np.abs(z).max())
+    assert np.max(np.abs(A @ zd - b)) <= TOL * max(1.0, np.abs(b).max(), np.abs(zd).max())
+    assert abs(out["energy"][0] - zd @ Q @ zd) <= TOL * abs(out["energy"][0])
+    gdC_flat = out["gdC"][0].reshape(N, 6, 3)[:, ::-1, :].transpose(0, 2, 1).reshape(-1)
+    np.testing.assert_allclose(gdC_flat, 2.0 * Q @ zd, rtol=0, atol=TOL * np.abs(Q @ zd).max())
+    gdT_ref = np.array([zd @ dQ[i] @ zd for i in range(N)])
+    np.testing.assert_allclose(out["gdT"][0], gdT_ref, rtol=0, atol=TOL * np.abs(gdT_ref).max())
+    gq, gT = handles[3].minco_propagate(head[None], tail[None], q[None], T[None], out["gdC"], out["gdT"])
+    gT_ref = np.array([z @ dQ[i] @ z + 2.0 * lam_a @ (dA[i] @ z) for i in range(N)])
+    gq_ref = -2.0 * lam_w.reshape(N - 1, 3)
+    np.testing.assert_allclose(gT[0], gT_ref, rtol=0, atol=2 * TOL * np.abs(gT_ref).max())
+    np.testing.assert_allclose(gq[0], gq_ref, rtol=0, atol=2 * TOL * np.abs(gq_ref).max())
+
+
 CASES = [  # (S, N, K, B, ragged, energy_only)
     (3, 8, 16, 4096, False, False),   # BASELINE config 3 shape
     (3, 8, 0, 4096, False, True),     # BASELINE config 2: energy only

@@ -4,8 +4,9 @@ The reference has no MINCO source and no tests for this path (SURVEY.md §0 F1, 
 oracle is pinned by independent restatements written here:
   (1) banded LU / solve / solveAdj vs numpy dense solves,
   (2) explicit S=3 rows typed from SURVEY.md Appendix A.2 vs the oracle's general-S rule,
-  (3) KKT of the REFERENCE QP formulation (Q of planner/qp_solver.hpp:223-234, boundary rows
-      :148-160, continuity rows :163-177, flatten idx :133) reproduces the MINCO coefficients,
+  (3) KKT of the REFERENCE QP formulation reproduces the MINCO coefficients -- with Q, A, b, G, h taken from
+      tests/golden/ref_qp_*.npz, i.e. built by the reference's own network/utils/min_traj_opt.py
+      (fill_eq_obj :377-533, fill_ineq :535-607; twin of planner/qp_solver.hpp:148-296), not typed here,
   (4) E == 2 * Trajectory<5>::getTrajCost(3) (gcopter/trajectory.hpp:396-420 constants),
   (5) finite differences on propogateGrad and on the whole cost functional,
   (6) smoothedL1 (gcopter/firi.hpp:60-84) and the tau<->T map properties,
@@ -127,46 +128,98 @@ def test_energy_s3_explicit_and_trajcost_identity(oracle):
     assert out["energy"] == pytest.approx(2.0 * half, rel=1e-13)
 
 
-def test_kkt_of_reference_qp_reproduces_minco(oracle):
-    """Reference QP (equality part) + waypoint rows == MINCO optimum; layouts of qp_solver.hpp."""
-    rng = np.random.default_rng(4)
-    S, N, d = 3, 5, 6
-    head, tail, q, T = rand_problem(rng, S, N)
-    nv = N * 3 * d
+# ---- reference-executed pins: matrices built by the reference's own fill_eq_obj / fill_ineq -----------------
+# tests/golden/ref_qp_*.npz are written by tests/golden/make_ref_qp_fixtures.py, which imports
+# /root/reference/network/utils/min_traj_opt.py unmodified (the Python twin of planner/qp_solver.hpp:119-360)
+# and stores the Q, A, b, G1, h1, G2, h2 it builds.  No reference constant is typed into this file.
+from ref_qp_util import REF_QP_CASES, load_ref_qp, ref_qp_problem, solve_ld, ref_qp_kkt  # noqa: E402
 
-    def t_state(t):  # get_t_state, qp_solver.hpp:90-116 (descending powers)
-        return np.array([[t**5, t**4, t**3, t**2, t, 1], [5 * t**4, 4 * t**3, 3 * t**2, 2 * t, 1, 0],
-                         [20 * t**3, 12 * t**2, 6 * t, 2, 0, 0]])
-    zero_A = np.zeros((3, 6)); zero_A[0, 5] = 1; zero_A[1, 4] = 1; zero_A[2, 3] = 2  # setOrder :76-78
-    rows, rhs = [], []
-    for a in range(3):  # boundary :148-160
-        for k in range(3):
-            r = np.zeros(nv); r[a * d:a * d + d] = zero_A[k]; rows.append(r); rhs.append(head[k, a])
-        for k in range(3):
-            r = np.zeros(nv); r[(N - 1) * 3 * d + a * d:(N - 1) * 3 * d + a * d + d] = t_state(T[N - 1])[k]
-            rows.append(r); rhs.append(tail[k, a])
-    for i in range(N - 1):  # continuity :163-177
+
+@pytest.mark.parametrize("name", REF_QP_CASES)
+def test_reference_qp_matrices_reproduce_minco(oracle, name):
+    """min 1/2 z^T Q z  s.t.  A z = b (the reference's boundary + continuity rows) and waypoint rows
+    == MINCO_S3NU coefficients of the oracle, in the reference's flatten order idx = i*3*d + j*d + k."""
+    c = load_ref_qp(name)
+    head, tail, q, T = ref_qp_problem(c, 5)
+    N, d = len(T), 6
+    Q, A, b = c["Q"], c["A"], c["b"]
+    nv = N * 3 * d
+    assert Q.shape == (nv, nv) and A.shape[1] == nv
+    W = np.zeros((3 * (N - 1), nv)); wq = np.zeros(3 * (N - 1))
+    for i in range(N - 1):
+        for a in range(3):      # start position of piece i+1, selected with the reference's own zero_A row 0
+            W[3 * i + a, (i + 1) * 3 * d + a * d:(i + 1) * 3 * d + a * d + d] = c["zero_A"][0]
+            wq[3 * i + a] = q[i, a]
+    Cm = np.vstack([A, W]); rhs = np.concatenate([b, wq]); m = Cm.shape[0]
+    KKT = np.block([[Q, Cm.T], [Cm, np.zeros((m, m))]])
+    z = solve_ld(KKT, np.concatenate([np.zeros(nv), rhs]))[:nv]
+    out = oracle.minco_forward(3, head, tail, q, T)
+    zo = out["flat"].reshape(-1)
+    np.testing.assert_allclose(zo, z, rtol=0, atol=1e-9 * np.abs(z).max())
+    assert 0.5 * zo @ Q @ zo == pytest.approx(out["energy"] / 2.0, rel=1e-10)
+    # the oracle's coefficients satisfy the reference's equality rows
+    assert np.max(np.abs(A @ zo - b)) <= 1e-9 * max(1.0, np.abs(b).max(), np.abs(zo).max())
+
+
+@pytest.mark.parametrize("name", REF_QP_CASES)
+def test_reference_qp_sensitivities_pin_energy_partials_and_propagate_grad(oracle, name):
+    """getEnergyPartialGradByCoeffs == 2 Q z, getEnergyPartialGradByTimes == z^T dQ/dT z, and propogateGrad ==
+    the KKT sensitivities of the reference's equality-constrained QP: with L = 1/2 z^T Q z + lam^T (C z - r),
+    d(1/2 z^T Q z)*/dT_i = 1/2 z^T dQ_i z + lam^T dC_i z and d/dq = -lam_waypoint.  dQ_i, dC_i are autograd
+    Jacobians through the reference's fill_eq_obj (fixture); E = 2 * (1/2 z^T Q z)."""
+    c = load_ref_qp(name)
+    head, tail, q, T = ref_qp_problem(c, 7)
+    N, d = len(T), 6
+    Q, A, b, dQ, dA = c["Q"], c["A"], c["b"], c["dQ"], c["dA"]
+    nv = N * 3 * d
+    W = np.zeros((3 * (N - 1), nv)); wq = np.zeros(3 * (N - 1))
+    for i in range(N - 1):
         for a in range(3):
-            col = i * 3 * d + a * d
-            for k in range(3):
-                r = np.zeros(nv); r[col:col + d] = t_state(T[i])[k]; r[col + 3 * d:col + 3 * d + d] = -zero_A[k]
-                rows.append(r); rhs.append(0.0)
-            r = np.zeros(nv); r[col + 3 * d:col + 3 * d + d] = zero_A[0]; rows.append(r); rhs.append(q[i, a])  # waypoint
-    Aeq = np.array(rows); beq = np.array(rhs)
-    Q = np.zeros((nv, nv))
-    for i in range(N):  # :223-234
-        t = T[i]
-        cq = np.array([[720 * t**5, 360 * t**4, 120 * t**3], [360 * t**4, 192 * t**3, 72 * t**2],
-                       [120 * t**3, 72 * t**2, 36 * t]])
-        for a in range(3):
-            col = i * 3 * d + a * d
-            Q[col:col + 3, col:col + 3] = cq
-    m = Aeq.shape[0]
-    KKT = np.block([[Q, Aeq.T], [Aeq, np.zeros((m, m))]])
-    z = np.linalg.lstsq(KKT, np.concatenate([np.zeros(nv), beq]), rcond=None)[0][:nv]
-    out = oracle.minco_forward(S, head, tail, q, T)
-    np.testing.assert_allclose(out["flat"].reshape(-1), z, rtol=0, atol=1e-7 * np.abs(z).max())
-    assert 0.5 * z @ Q @ z == pytest.approx(out["energy"] / 2.0, rel=1e-8)
+            W[3 * i + a, (i + 1) * 3 * d + a * d:(i + 1) * 3 * d + a * d + d] = c["zero_A"][0]
+            wq[3 * i + a] = q[i, a]
+    Cm = np.vstack([A, W]); rhs = np.concatenate([b, wq]); m = Cm.shape[0]
+    KKT = np.block([[Q, Cm.T], [Cm, np.zeros((m, m))]])
+    sol = solve_ld(KKT, np.concatenate([np.zeros(nv), rhs]))
+    z, lam = sol[:nv], sol[nv:]
+    out = oracle.minco_forward(3, head, tail, q, T)
+    zo = out["flat"].reshape(-1)
+    # partials at the oracle's own coefficients; flat[i][a][k] = coeffs[6i + 5 - k][a]
+    gdC_flat = out["gdC"].reshape(N, 6, 3)[:, ::-1, :].transpose(0, 2, 1).reshape(-1)
+    np.testing.assert_allclose(gdC_flat, 2.0 * Q @ zo, rtol=0, atol=1e-10 * np.abs(Q @ zo).max())
+    gdT_ref = np.array([zo @ dQ[i] @ zo for i in range(N)])
+    np.testing.assert_allclose(out["gdT"], gdT_ref, rtol=1e-10, atol=1e-10 * np.abs(gdT_ref).max())
+    # total derivatives of the optimal energy
+    gq, gT = oracle.minco_propagate(3, head, tail, q, T, out["gdC"], out["gdT"])
+    gT_ref = np.array([z @ dQ[i] @ z + 2.0 * lam[:A.shape[0]] @ (dA[i] @ z) for i in range(N)])
+    gq_ref = -2.0 * lam[A.shape[0]:].reshape(N - 1, 3)
+    np.testing.assert_allclose(gT, gT_ref, rtol=0, atol=2e-9 * np.abs(gT_ref).max())
+    np.testing.assert_allclose(gq, gq_ref, rtol=0, atol=2e-9 * np.abs(gq_ref).max())
+
+
+@pytest.mark.parametrize("name", REF_QP_CASES)
+def test_reference_qp_inequality_rows_pin_sampling_layout(oracle, name):
+    """G1 z - h1 (corridor) and G2 z - h2 (+-v, +-a boxes) of the reference, evaluated on the oracle's
+    coefficients, equal the residuals computed from the polynomial pieces at t = j*T_i/res, j = 0..res-1
+    (left end points, qp_solver.hpp:252-296 / min_traj_opt.py:553-607)."""
+    c = load_ref_qp(name)
+    head, tail, q, T = ref_qp_problem(c, 6)
+    N, res = len(T), int(c["res"])
+    out = oracle.minco_forward(3, head, tail, q, T)
+    zo = out["flat"].reshape(-1)
+    co = out["coeffs"].reshape(N, 6, 3)               # ascending powers
+    r1 = c["G1"] @ zo - c["h1"]; r2 = c["G2"] @ zo - c["h2"]
+    e1, e2 = [], []
+    for i in range(N):
+        hp = c["hpolys"][:, :, i]
+        for j in range(res):
+            t = j * T[i] / res
+            p = beta(t, 0, 6) @ co[i]; v = beta(t, 1, 6) @ co[i]; a = beta(t, 2, 6) @ co[i]
+            e1.extend(hp[:, :3] @ p - hp[:, 3])
+            for ax in range(3):
+                e2.extend([v[ax] - 4.0, a[ax] - 6.0, -v[ax] - 4.0, -a[ax] - 6.0])
+    scale = max(1.0, np.abs(zo).max())
+    np.testing.assert_allclose(r1, np.array(e1), rtol=0, atol=1e-10 * scale)
+    np.testing.assert_allclose(r2, np.array(e2), rtol=0, atol=1e-10 * scale)
 
 
 @pytest.mark.parametrize("S,N", [(3, 2), (3, 5), (3, 8), (4, 8), (3, 16)])
