@@ -15,7 +15,7 @@ from allocnet_b200 import params as P
 from allocnet_b200.params import default_params, energy_only
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "s[34]_*.npz")))   # ref_qp_*.npz: tests/ref_qp_util.py
 IDS = [os.path.basename(f)[:-4] for f in FILES]
 
 
