@@ -34,7 +34,7 @@ SYMBOLS = [
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
     "mincob_max_rates", "mincob_max_rates_device", "mincob_minco_forward_device", "mincob_minco_propagate_device",
-    "mincob_optimize_sharded_local", "mincob_gathered_device",
+    "mincob_optimize_sharded_local", "mincob_gathered_device", "mincob_last_mapping",
 ]
 
 
@@ -88,6 +88,8 @@ def load_library() -> C.CDLL:
     L.mincob_minco_forward_device.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 9
     L.mincob_minco_propagate_device.argtypes = [_vp, C.c_int, C.c_int] + [_vp] * 8
     L.mincob_max_rates_device.argtypes = [_vp, _vp, _vp, _vp]
+    if hasattr(L, "mincob_last_mapping"):   # absent from older builds selected with MINCOB_LIBRARY (A/B runs)
+        L.mincob_last_mapping.argtypes = [_vp, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -124,6 +126,12 @@ class MincoBatch:
         self._keep = None
 
     # -- plumbing -------------------------------------------------------------------------
+    @staticmethod
+    def _want(a, shape, name):
+        if tuple(a.shape) != tuple(shape):
+            raise MincobError(f"{name} must have shape {tuple(shape)}, got {tuple(a.shape)}")
+        return a
+
     def _check(self, rc):
         if rc != 0:
             raise MincobError(f"{self.L.mincob_strerror(rc).decode()}: {self.L.mincob_last_error(self.h).decode()} (rc={rc})")
@@ -152,7 +160,10 @@ class MincoBatch:
         self.params = params
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self.L.mincob_set_stream(self.h, _vp(cuda_stream) if cuda_stream else None))
+        """None = the handle's own non-blocking stream.  An integer is passed through as the cudaStream_t; note that
+        torch's default stream reports 0, which the C-ABI also reads as "own stream": pass cudaStreamLegacy (0x1) or
+        cudaStreamPerThread (0x2) to run on a default stream (allocnet_b200/autograd.py does)."""
+        self._check(self.L.mincob_set_stream(self.h, _vp(cuda_stream) if cuda_stream is not None else None))
 
     def synchronize(self):
         self._check(self.L.mincob_synchronize(self.h))
@@ -162,16 +173,25 @@ class MincoBatch:
         self._check(self.L.mincob_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def last_mapping(self) -> int:
+        """params.MAP_THROUGHPUT / MAP_LATENCY: what the last optimize call launched."""
+        m = C.c_int(0)
+        self._check(self.L.mincob_last_mapping(self.h, C.byref(m)))
+        return int(m.value)
+
     # -- problems -------------------------------------------------------------------------
     def set_problems(self, pb):
         """pb: allocnet_b200.synth.ProblemBatch (host numpy arrays in the C-ABI layouts)."""
         if pb.S != self.S:
             raise MincobError(f"problem batch has S={pb.S}, handle has S={self.S}")
-        hp = pb.hpolys if pb.K > 0 else None
-        hr = pb.hrows if pb.K > 0 else None
-        self._check(self.L.mincob_set_problems(self.h, pb.B, pb.N, pb.K, _np_ptr(pb.head), _np_ptr(pb.tail),
-                                               _np_ptr(hp), _np_ptr(hr)))
-        self.B, self.N, self.K = pb.B, pb.N, pb.K
+        B, N, K, S = int(pb.B), int(pb.N), int(pb.K), self.S
+        # the C side reads exactly B*S*3 / B*N*K*4 doubles and B*N int32: coerce (dtype, contiguity) and check shapes here
+        head = self._want(_f64(pb.head), (B, S, 3), "head")
+        tail = self._want(_f64(pb.tail), (B, S, 3), "tail")
+        hp = self._want(_f64(pb.hpolys), (B, N, K, 4), "hpolys") if K > 0 else None
+        hr = self._want(np.ascontiguousarray(pb.hrows, dtype=np.int32), (B, N), "hrows") if K > 0 else None
+        self._check(self.L.mincob_set_problems(self.h, B, N, K, _np_ptr(head), _np_ptr(tail), _np_ptr(hp), _np_ptr(hr)))
+        self.B, self.N, self.K = B, N, K
 
     def set_problems_device(self, B, N, K, head, tail, hpolys=None, hrows=None):
         self._check(self.L.mincob_set_problems_device(self.h, B, N, K, _dev_ptr(head), _dev_ptr(tail),
@@ -238,7 +258,8 @@ class MincoBatch:
     # -- feasibility report (sampled Piece::getMaxVelRate / getMaxAccRate / corridor residual) ------
     def check_feasibility(self, coeffs, T, samples: int = 64):
         """-> [B][4]: max |v|, max |a|, max |j|, max_k(n_k.p + d_k) over samples+1 points per piece."""
-        coeffs, T = _f64(coeffs), _f64(T)
+        coeffs = self._want(_f64(coeffs), (self.B, self.N, 3, 2 * self.S), "coeffs")
+        T = self._want(_f64(T), (self.B, self.N), "T")
         rep = np.zeros((self.B, 4))
         self._check(self.L.mincob_check_feasibility(self.h, _np_ptr(coeffs), _np_ptr(T), int(samples), _np_ptr(rep)))
         return rep
@@ -259,8 +280,9 @@ class MincoBatch:
 
     def max_rates(self, coeffs, T):
         """[B][3] exact max |v|, |a|, |j| per trajectory (Trajectory<D>::getMaxVelRate / getMaxAccRate, + jerk)."""
-        coeffs = _f64(coeffs); T = _f64(T)
-        rates = np.empty((coeffs.shape[0], 3), dtype=np.float64)
+        coeffs = self._want(_f64(coeffs), (self.B, self.N, 3, 2 * self.S), "coeffs")
+        T = self._want(_f64(T), (self.B, self.N), "T")
+        rates = np.empty((self.B, 3), dtype=np.float64)
         self._check(self.L.mincob_max_rates(self.h, _np_ptr(coeffs), _np_ptr(T), _np_ptr(rates)))
         return rates
 

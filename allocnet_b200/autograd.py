@@ -20,6 +20,17 @@ import torch
 from .api import MincoBatch
 
 
+# cudaStreamLegacy ((cudaStream_t)0x1): the explicit handle of the legacy default stream.  torch reports its default
+# stream as 0, which the C-ABI reads as "the handle's own (non-blocking) stream" -- kernels there are NOT ordered with
+# torch's default-stream work, so q / T could be read before they are written and the outputs before they are filled.
+_CUDA_STREAM_LEGACY = 0x1
+
+
+def _bind_to_torch_stream(mb: MincoBatch, device) -> None:
+    s = torch.cuda.current_stream(device).cuda_stream
+    mb.set_stream(s if s else _CUDA_STREAM_LEGACY)
+
+
 class _MincoFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mb: MincoBatch, head, tail, q, T):
@@ -33,7 +44,7 @@ class _MincoFunction(torch.autograd.Function):
         energy = torch.empty(B, dtype=torch.float64, device=T.device)
         gdC = torch.empty_like(coeffs)
         gdT = torch.empty(B, N, dtype=torch.float64, device=T.device)
-        mb.set_stream(torch.cuda.current_stream(T.device).cuda_stream)
+        _bind_to_torch_stream(mb, T.device)
         mb.minco_forward_device(B, N, head, tail, q, T, coeffs_asc=coeffs, energy=energy, gdC=gdC, gdT=gdT)
         ctx.mb = mb
         ctx.save_for_backward(head, tail, q, T, gdC, gdT)
@@ -52,7 +63,7 @@ class _MincoFunction(torch.autograd.Function):
             pt += g_energy[:, None] * gdT
         gq = torch.zeros(B, max(N - 1, 1), 3, dtype=torch.float64, device=T.device)
         gT = torch.empty(B, N, dtype=torch.float64, device=T.device)
-        mb.set_stream(torch.cuda.current_stream(T.device).cuda_stream)
+        _bind_to_torch_stream(mb, T.device)
         mb.minco_propagate_device(B, N, head, tail, q, T, pc, pt, gq, gT)
         return None, None, None, (gq if N > 1 else None), gT
 

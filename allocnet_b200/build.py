@@ -1,6 +1,6 @@
 """In-tree build of allocnet_b200/libmincob.so (nvcc, sm_100a only).
 
-Six (S, LPT) kernel objects + the host API object are compiled in parallel and linked into one
+Eight (S, LPT) kernel objects + the host API object are compiled in parallel and linked into one
 shared library next to this file, so it travels to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
@@ -17,11 +17,14 @@ OBJ = os.environ.get("MINCOB_BUILD_DIR") or os.path.join(HERE, "build")
 LIB = os.environ.get("MINCOB_BUILD_OUT") or os.path.join(HERE, "libmincob.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-INST = [(S, L) for S in (3, 4) for L in (8, 16, 32)]
+INST = [(S, L) for S in (3, 4) for L in (5, 8, 16, 32)]
 # resident blocks per SM the optimize kernel is compiled for (caps registers per thread); override for
 # experiments with MINCOB_MINB3 / MINCOB_MINB4 in the environment
 EXTRA = os.environ.get("MINCOB_EXTRA_FLAGS", "").split()
 MINB = {3: int(os.environ.get("MINCOB_MINB3", "3")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
+# threads per block per LPT: the LPT = 5 objects (six trajectories per warp) use one-warp blocks so that shared memory,
+# not the block granularity, decides how many warps fit (11 per SM at N = 5, K = 16); MINB scales to the same register cap
+THREADS = {5: int(os.environ.get("MINCOB_THREADS5", "32"))}
 
 
 def _nvcc():
@@ -59,7 +62,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     for S, L in INST:
         o = os.path.join(OBJ, f"kernels_s{S}_l{L}.o")
-        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={MINB.get(S, 2)}", *EXTRA, "-c",
+        thr = THREADS.get(L, 128)
+        minb = MINB.get(S, 2) * 128 // thr
+        jobs.append(([nvcc, *ARCH, *FLAGS, f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={minb}", f"-DMINCOB_THREADS={thr}", *EXTRA, "-c",
                       os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
     o = os.path.join(OBJ, "mincob.o")
     jobs.append(([nvcc, *ARCH, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))

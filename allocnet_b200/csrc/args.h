@@ -34,6 +34,8 @@ struct DevParams {
     double mu, w_pos, w_vel, w_acc, w_jerk, vmax2, amax2, jmax2, rho;
     double imu, ikap;   // 1/mu, 1/kappa (an fp64 division is ~30 instructions on the device)
     int penalties;  // 0: energy-only fast path (all weights zero)
+    int mapping;    // MINCOB_MAP_AUTO / _THROUGHPUT / _LATENCY (include/mincob.h)
+    int freeze;     // 1: MINCOB_FLAG_FREEZE_TIMES -- durations stay as given (d/dtau = 0), waypoints only
     // L-BFGS (gcopter/lbfgs.hpp:15-129)
     int mem, past, max_iter, max_ls;
     double g_eps, delta, min_step, max_step, f_dec, s_curv, cautious, mach_prec;

@@ -18,14 +18,16 @@ namespace mincob {
 template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int propagate) {
     constexpr int D = 2 * S, b = S - 1;
-    const int lig = (threadIdx.x & 31) % LPT;
+    using LN = Lanes<LPT>;
+    constexpr int GPB = (THREADS / 32) * LN::GPW;
+    const int lig = LN::lig();
     const unsigned mask = 0xffffffffu;  // uniform control flow: whole warp participates in every shuffle
     const int N = a.N;
-    const int groups = gridDim.x * (THREADS / LPT);
+    const int groups = gridDim.x * GPB;
     const int rounds = (a.B + groups - 1) / groups;
-    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    int p = blockIdx.x * GPB + LN::gib();
     for (int it = 0; it < rounds; ++it, p += groups) {
-        const bool live = p < a.B;
+        const bool live = LN::real() && p < a.B;
         const int pp = live ? p : 0;
         const int Ne = live ? N : 0;
         const bool active = lig < Ne;
@@ -89,14 +91,16 @@ __global__ void __launch_bounds__(THREADS) minco_kernel(const MincoArgs a, int p
 template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) check_kernel(const CheckArgs a) {
     constexpr int D = 2 * S;
-    const int lig = (threadIdx.x & 31) % LPT;
+    using LN = Lanes<LPT>;
+    constexpr int GPB = (THREADS / 32) * LN::GPW;
+    const int lig = LN::lig();
     const unsigned mask = 0xffffffffu;
     const int N = a.N;
-    const int groups = gridDim.x * (THREADS / LPT);
+    const int groups = gridDim.x * GPB;
     const int rounds = (a.B + groups - 1) / groups;
-    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    int p = blockIdx.x * GPB + LN::gib();
     for (int it = 0; it < rounds; ++it, p += groups) {
-        const bool live = p < a.B && lig < N;
+        const bool live = LN::real() && p < a.B && lig < N;
         double vmax = 0.0, amax = 0.0, jmax = 0.0, cmax = -1.0e300;
         if (live) {
             const double *c = a.coeffs + ((size_t)p * N + lig) * 3 * D;   // [3][2S], k = 0 highest power
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(THREADS) check_kernel(const CheckArgs a) {
         }
         vmax = group_max<LPT>(mask, vmax); amax = group_max<LPT>(mask, amax);
         jmax = group_max<LPT>(mask, jmax); cmax = group_max<LPT>(mask, cmax);
-        if (p < a.B && lig == 0) {
+        if (LN::real() && p < a.B && lig == 0) {
             double *o = a.out + (size_t)p * 4;
             o[0] = sqrt(vmax); o[1] = sqrt(amax); o[2] = sqrt(jmax); o[3] = cmax;
         }
@@ -162,14 +166,16 @@ __device__ __forceinline__ void deriv3(const double *c, double t, int d, double 
 template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) maxrate_kernel(const RateArgs a) {
     constexpr int D = 2 * S;
-    const int lig = (threadIdx.x & 31) % LPT;
+    using LN = Lanes<LPT>;
+    constexpr int GPB = (THREADS / 32) * LN::GPW;
+    const int lig = LN::lig();
     const unsigned mask = 0xffffffffu;
     const int N = a.N;
-    const int groups = gridDim.x * (THREADS / LPT);
+    const int groups = gridDim.x * GPB;
     const int rounds = (a.B + groups - 1) / groups;
-    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    int p = blockIdx.x * GPB + LN::gib();
     for (int it = 0; it < rounds; ++it, p += groups) {
-        const bool live = p < a.B && lig < N;
+        const bool live = LN::real() && p < a.B && lig < N;
         double best[3] = {0.0, 0.0, 0.0};
         if (live) {
             double c[3 * D];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(THREADS) maxrate_kernel(const RateArgs a) {
         }
 #pragma unroll
         for (int d = 0; d < 3; ++d) best[d] = group_max<LPT>(mask, best[d]);
-        if (p < a.B && lig == 0) {
+        if (LN::real() && p < a.B && lig == 0) {
             double *o = a.out + (size_t)p * 3;
             o[0] = sqrt(best[0]); o[1] = sqrt(best[1]); o[2] = sqrt(best[2]);
         }
@@ -220,9 +226,12 @@ using namespace mincob;
 #ifndef MINCOB_THREADS
 #define MINCOB_THREADS 128   // threads per block of every kernel here (experiments: 256 / 384 with MINCOB_LOCKSTEP)
 #endif
-constexpr int S = MINCOB_S, LPT = MINCOB_LPT, THREADS = MINCOB_THREADS, GPB = THREADS / LPT;
+constexpr int S = MINCOB_S, LPT = MINCOB_LPT, THREADS = MINCOB_THREADS;
+constexpr int WARPS = THREADS / 32;
+constexpr int GPB = WARPS * Lanes<LPT>::GPW;   // trajectories per block (throughput mapping)
+constexpr int SPB = WARPS * Lanes<LPT>::SPW;   // group slots per block (GPB + one dummy group per warp when LPT does not divide 32)
 
-LaunchResult ok(cudaError_t e) { return LaunchResult{e, 0, 0}; }
+LaunchResult ok(cudaError_t e) { return LaunchResult{e, 0, 0, 0}; }
 
 LaunchResult launch_evaluate(cudaStream_t st, int sm_count, const DevParams &dp, const BatchArgs &a) {
     int blocks = (a.B + GPB - 1) / GPB;
@@ -235,7 +244,7 @@ LaunchResult launch_evaluate(cudaStream_t st, int sm_count, const DevParams &dp,
 // Shared memory per block and grid of the persistent optimize kernel.  Half-planes are staged in
 // shared memory when at least MINCOB_MINB blocks per SM still fit; otherwise they are read from global.
 struct OptPlan {
-    int psmem, blocks;
+    int psmem, rep, blocks;
     size_t smem, hist_bytes, mult_bytes, park_bytes;
     int code;
     cudaError_t err;
@@ -245,45 +254,71 @@ struct OptPlan {
 #define MINCOB_FASTMEM 8
 #endif
 constexpr int FASTMEM = MINCOB_FASTMEM;   // 0: every depth takes the rolled loops (experiments)
+using OptKernel = void (*)(const DevParams, const BatchArgs);
 template <bool PSMEM, int MEM>
-static int blocks_per_sm(size_t smem, cudaError_t &e) {
-    auto kern = optimize_kernel<S, LPT, THREADS, PSMEM, MEM>;
+static OptKernel opt_kernel(bool rep) {
+    if (rep) return optimize_kernel<S, LPT, THREADS, PSMEM, MEM, true>;
+    return optimize_kernel<S, LPT, THREADS, PSMEM, MEM, false>;
+}
+static OptKernel pick_kernel(bool psmem, int mem, bool rep) {
+    if (mem == FASTMEM) return psmem ? opt_kernel<true, FASTMEM>(rep) : opt_kernel<false, FASTMEM>(rep);
+    return psmem ? opt_kernel<true, 0>(rep) : opt_kernel<false, 0>(rep);
+}
+static int blocks_per_sm(OptKernel kern, size_t smem, cudaError_t &e) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { e = cudaSuccess; (void)cudaGetLastError(); return 0; }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
     return e == cudaSuccess ? per_sm : 0;
 }
+// mapping: MINCOB_MAP_AUTO picks the latency mapping (one warp per trajectory) when the batch cannot give every
+// resident warp a trajectory of its own anyway; the results of the two mappings agree to rounding (the penalty
+// samples are added in a different order), so a caller that needs run-to-run identical bits across batch sizes
+// pins the mapping in mincob_params.
+static size_t smem_bytes(int N, int K, const DevParams &dp, int psmem) {
+    return ((size_t)GPB * optimize_group_doubles(S, N, K, dp.mem, dp.past, psmem, LPT) +
+            (size_t)(SPB - GPB) * optimize_small_doubles(S, dp.mem, dp.past, LPT)) * sizeof(double);
+}
 static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs &a) {
-    OptPlan pl{0, 0, 0, 0, 0, 0, 0, cudaSuccess};
+    OptPlan pl{0, 0, 0, 0, 0, 0, 0, 0, cudaSuccess};
     const bool have = a.hpolys && a.hrows && a.K > 0;
+    const bool can_rep = Lanes<LPT>::GPW > 1;
     int per_sm = 0;
+    // occupancy does not depend on REP (same registers cap, same shared memory): plan with the throughput kernel
     if (have && dp.penalties) {
-        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 1, LPT) * sizeof(double);
-        per_sm = dp.mem == FASTMEM ? blocks_per_sm<true, FASTMEM>(pl.smem, pl.err) : blocks_per_sm<true, 0>(pl.smem, pl.err);
+        pl.smem = smem_bytes(a.N, a.K, dp, 1);
+        per_sm = blocks_per_sm(pick_kernel(true, dp.mem, false), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
-        pl.psmem = per_sm >= MINCOB_MINB || per_sm >= 2;
+        pl.psmem = per_sm >= MINCOB_MINB || per_sm * WARPS >= 8;   // staging must leave at least 8 warps per SM resident
 #ifdef MINCOB_GLOBAL_PLANES   // experiment: never stage half-planes in shared memory (occupancy then depends on registers only)
         pl.psmem = 0;
 #endif
     }
     if (!pl.psmem) {
-        pl.smem = (size_t)GPB * optimize_group_doubles(S, a.N, a.K, dp.mem, dp.past, 0, LPT) * sizeof(double);
-        per_sm = dp.mem == FASTMEM ? blocks_per_sm<false, FASTMEM>(pl.smem, pl.err) : blocks_per_sm<false, 0>(pl.smem, pl.err);
+        pl.smem = smem_bytes(a.N, a.K, dp, 0);
+        per_sm = blocks_per_sm(pick_kernel(false, dp.mem, false), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
     }
     if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
     pl.blocks = per_sm * sm_count;
-    const int need = (a.B + GPB - 1) / GPB;
+    pl.rep = can_rep && (dp.mapping == MINCOB_MAP_LATENCY || (dp.mapping == MINCOB_MAP_AUTO && a.B <= pl.blocks * WARPS));
+    if (pl.rep) {
+        per_sm = blocks_per_sm(pick_kernel(pl.psmem, dp.mem, true), pl.smem, pl.err);
+        if (pl.err != cudaSuccess) return pl;
+        if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
+        pl.blocks = per_sm * sm_count;
+    }
+    const int per_block = pl.rep ? WARPS : GPB;
+    const int need = (a.B + per_block - 1) / per_block;
     if (pl.blocks > need) pl.blocks = need;
-    pl.hist_bytes = (size_t)pl.blocks * GPB * dp.mem * LPT * 8 * sizeof(double);
+    pl.hist_bytes = (size_t)pl.blocks * SPB * dp.mem * LPT * 8 * sizeof(double);
     pl.hist_bytes = (pl.hist_bytes + 255) & ~(size_t)255;
     pl.mult_bytes = (size_t)pl.blocks * SplineReg<S, LPT>::NM * THREADS * sizeof(double);
     pl.park_bytes = (size_t)pl.blocks * 12 * THREADS * sizeof(double);
     return pl;
 }
 
-// one allocation: [history slabs | multiplier slabs]
+// one allocation: [history slabs | multiplier slabs | parked state]; sized for the larger of the two mappings
 size_t optimize_scratch(int sm_count, const DevParams &dp, const BatchArgs &a) {
     const OptPlan pl = plan_optimize(sm_count, dp, a);
     return pl.hist_bytes + pl.mult_bytes + pl.park_bytes;
@@ -292,7 +327,7 @@ size_t optimize_scratch(int sm_count, const DevParams &dp, const BatchArgs &a) {
 LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp, const BatchArgs &a) {
     const OptPlan pl = plan_optimize(sm_count, dp, a);
     if (pl.err != cudaSuccess) return ok(pl.err);
-    if (pl.code) return LaunchResult{cudaSuccess, pl.code, pl.smem};
+    if (pl.code) return LaunchResult{cudaSuccess, pl.code, pl.smem, 0};
     cudaError_t e;
     if ((e = cudaMemsetAsync(a.counter, 0, sizeof(int), st)) != cudaSuccess) return ok(e);
     if ((e = cudaMemsetAsync(a.total_evals, 0, 128 * sizeof(unsigned long long), st)) != cudaSuccess) return ok(e);
@@ -303,14 +338,10 @@ LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp,
     BatchArgs b = a;
     b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
     b.lpark = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes + pl.mult_bytes);
-    if (dp.mem == FASTMEM) {
-        if (pl.psmem) optimize_kernel<S, LPT, THREADS, true, FASTMEM><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
-        else optimize_kernel<S, LPT, THREADS, false, FASTMEM><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
-    } else {
-        if (pl.psmem) optimize_kernel<S, LPT, THREADS, true, 0><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
-        else optimize_kernel<S, LPT, THREADS, false, 0><<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
-    }
-    return ok(cudaGetLastError());
+    pick_kernel(pl.psmem, dp.mem, pl.rep)<<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    LaunchResult r = ok(cudaGetLastError());
+    r.mapping = pl.rep ? MINCOB_MAP_LATENCY : MINCOB_MAP_THROUGHPUT;
+    return r;
 }
 
 LaunchResult launch_minco(cudaStream_t st, int sm_count, const MincoArgs &a, int propagate) {

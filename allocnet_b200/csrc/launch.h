@@ -9,6 +9,7 @@ struct LaunchResult {
     cudaError_t err;
     int code;      // 0 or MINCOB_E_INVALID when the kernel cannot be resident
     size_t smem;
+    int mapping;   // optimize: MINCOB_MAP_THROUGHPUT / MINCOB_MAP_LATENCY actually launched
 };
 struct LaunchTable {
     LaunchResult (*evaluate)(cudaStream_t, int sm_count, const DevParams &, const BatchArgs &);
@@ -20,6 +21,8 @@ struct LaunchTable {
     LaunchResult (*maxrates)(cudaStream_t, int sm_count, const RateArgs &);
 };
 }  // namespace mincob
+const mincob::LaunchTable *mincob_table_3_5();
+const mincob::LaunchTable *mincob_table_4_5();
 const mincob::LaunchTable *mincob_table_3_8();
 const mincob::LaunchTable *mincob_table_3_16();
 const mincob::LaunchTable *mincob_table_3_32();

@@ -112,12 +112,15 @@ __device__ __noinline__ void emit_trajectory(unsigned, int lig, int N, int round
 
 enum { PH_FETCH = 0, PH_FIRST = 1, PH_LS = 2, PH_IDLE = 3 };
 
-// doubles of shared memory one group needs (host and device must agree)
-__host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m, int past, int planes_in_smem, int lpt) {
-    const int planes = planes_in_smem ? N * K * 4 : 0;
+// doubles of shared memory one group needs (host and device must agree): the plane stage, then the small part
+// (head/tail, alpha / y.s / past-f rings, parking).  The dummy group of a warp (LPT not a power of two) only
+// gets a small part.
+__host__ __device__ inline int optimize_small_doubles(int S, int m, int past, int lpt) {
     int small = 2 * S * 3 + 2 * m + (past > 0 ? past : 1) + 12 + 4 * lpt;   // + parking: scalars (7 doubles, 8 ints), d
-    small = (small + 3) & ~3;                      // keep every group's plane stage 32-byte aligned
-    return planes + small;
+    return (small + 3) & ~3;                       // keep every group's plane stage 32-byte aligned
+}
+__host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m, int past, int planes_in_smem, int lpt) {
+    return (planes_in_smem ? N * K * 4 : 0) + optimize_small_doubles(S, m, past, lpt);
 }
 
 // Control flow of one trip (all 32 lanes of the warp walk it together; the 32/LPT groups differ only
@@ -134,18 +137,26 @@ __host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m
 // recursion is unrolled over registers, the first MINCOB_HDEP history pairs are requested right after the
 // evaluation (their L2 latency is covered by the reductions and the scalar decisions) and the others
 // MINCOB_HDEP steps ahead of their use.  MEM == 0: any depth, rolled loops with two slots in flight.
-template <int S, int LPT, int THREADS, bool PSMEM, int MEM>
+// REP: latency mapping, "one warp per trajectory" (BASELINE.json north_star): the GPW groups of a warp fetch the SAME
+// problem and run the same state machine on bitwise identical state; only the penalty samples are split among them
+// (cost_functional<.., REP>).  Used when the batch is too small to fill the device with one group per problem.
+template <int S, int LPT, int THREADS, bool PSMEM, int MEM, bool REP>
 __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const DevParams P, const BatchArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lig = (threadIdx.x & 31) % LPT;
-    const int gib = threadIdx.x / LPT;
+    using LN = Lanes<LPT>;
+    constexpr int SPB = (THREADS / 32) * LN::SPW;   // group slots per block (real groups + dummy groups)
+    const int lig = LN::lig();
+    const int gib = LN::slot();
     const int N = a.N, K = a.K, n = N + 3 * (N - 1), m = MEM > 0 ? MEM : P.mem, past = P.past;
     const int rounds = N > 2 ? N - 2 : 0;   // lane-to-lane sweeps of the block solve (warp-uniform)
 
     extern __shared__ __align__(32) double smem[];
-    double *grp = smem + (size_t)gib * optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0, LPT);
-    double *planes_s = grp;                                  // [K][N][4] when PSMEM
-    double *ht = grp + (PSMEM ? N * K * 4 : 0);              // head [S][3], tail [S][3]
+    // real groups first (plane stage + small part each), then one small part per dummy group
+    constexpr int GPBK = (THREADS / 32) * LN::GPW;
+    const int gdoubles = optimize_group_doubles(S, N, K, m, past, PSMEM ? 1 : 0, LPT);
+    double *planes_s = smem + (size_t)(LN::real() ? LN::gib() : 0) * gdoubles;   // [K][N][4] when PSMEM
+    double *ht = LN::real() ? planes_s + (PSMEM ? N * K * 4 : 0)                  // head [S][3], tail [S][3]
+                            : smem + (size_t)GPBK * gdoubles + (size_t)(threadIdx.x >> 5) * optimize_small_doubles(S, m, past, LPT);
     double *alpha = ht + 2 * S * 3;
     double *ysv = alpha + m;
     double *pf = ysv + m;
@@ -153,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
     int *park_i = reinterpret_cast<int *>(park_d + 8);
     double *park_dir = park_d + 12 + lig;                     // d of this lane (needed first after the evaluation): [4][LPT]
     // history slab of this group: [m][LPT][8] = (s0..s3, y0..y3) of lane lig in slot j
-    double *hist = a.hist + ((size_t)blockIdx.x * (THREADS / LPT) + gib) * ((size_t)m * LPT * 8) + (size_t)lig * 8;
+    double *hist = a.hist + ((size_t)blockIdx.x * SPB + gib) * ((size_t)m * LPT * 8) + (size_t)lig * 8;
 
     // block-solve multipliers of the current evaluation: slot i of thread t at mult[(block*NM + i)*THREADS + t]
     GlobalStore mstore;
@@ -169,7 +180,10 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
         atomicMin(a.total_evals + 3, t);
     }
 #endif
-    int phase = PH_FETCH, prob = 0;
+    int phase = LN::real() ? PH_FETCH : PH_IDLE, prob = 0;   // the dummy group (LPT not a power of two) never owns a problem
+    if (!LN::real()) {
+        for (int i = lig; i < 2 * S * 3; i += LPT) ht[i] = 0.0;
+    }
     ProblemView pv;
     pv.head = ht; pv.tail = ht + S * 3; pv.planes = nullptr; pv.rstride = 4; pv.rows = 0;
     double x[4] = {0, 0, 0, 0}, g[4], xp[4] = {0, 0, 0, 0}, gp[4] = {0, 0, 0, 0}, d[4] = {0, 0, 0, 0};
@@ -183,8 +197,13 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
         if (__any_sync(FULL, phase == PH_FETCH)) {
             const bool want = phase == PH_FETCH;
             int p = 0;
-            if (want && lig == 0) p = atomicAdd(a.counter, 1);
-            p = __shfl_sync(FULL, p, 0, LPT);
+            if (REP) {   // the replicas of a warp always finish together: one ticket for the warp
+                if (want && LN::lane() == 0) p = atomicAdd(a.counter, 1);
+                p = __shfl_sync(FULL, p, 0);
+            } else {
+                if (want && lig == 0) p = atomicAdd(a.counter, 1);
+                p = group_first<LPT>(FULL, p);
+            }
             if (want) {
                 if (p >= a.B) {
 #ifdef MINCOB_TIMING
@@ -257,9 +276,9 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #pragma unroll
             for (int i = 0; i < 4; ++i) { xp[i] = lstore.get(i); gp[i] = lstore.get(4 + i); d[i] = park_dir[i * LPT]; }
         };
-        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, unpark);
+        const double f = cost_functional<S, LPT, PSMEM, GlobalStore, REP>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, unpark);
 #else
-        const double f = cost_functional<S, LPT, PSMEM>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq);
+        const double f = cost_functional<S, LPT, PSMEM, GlobalStore, REP>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq);
 #endif
         g[1] = gq[0]; g[2] = gq[1]; g[3] = gq[2];
 #if MINCOB_PARK
@@ -529,7 +548,8 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 
         // ---- retire ----------------------------------------------------------------------------
         if (__any_sync(FULL, finish != 0)) {
-            if (finish) {
+            const bool writer = !REP || LN::giw() == 0;   // replicas hold identical results: replica 0 writes them
+            if (finish && writer) {
                 store_x<LPT>(a.x + (size_t)prob * n, N, lig, x);
                 if (lig == 0) {
                     if (a.f_out) a.f_out[prob] = fx;
@@ -541,8 +561,8 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             }
             if (a.coeffs || a.T)
                 emit_trajectory<S, LPT>(FULL, lig, finish ? N : 0, rounds, pv, x,
-                                        (finish && a.coeffs) ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
-                                        (finish && a.T) ? a.T + (size_t)prob * N : nullptr);
+                                        (finish && writer && a.coeffs) ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
+                                        (finish && writer && a.T) ? a.T + (size_t)prob * N : nullptr);
             if (finish) phase = PH_FETCH;
         }
     }
@@ -558,13 +578,15 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 // One launch = the lbfgs_evaluate_t callback body for every problem of the batch.
 template <int S, int LPT, int THREADS>
 __global__ void __launch_bounds__(THREADS) evaluate_kernel(const DevParams P, const BatchArgs a) {
-    const int lig = (threadIdx.x & 31) % LPT;
+    using LN = Lanes<LPT>;
+    constexpr int GPB = (THREADS / 32) * LN::GPW;
+    const int lig = LN::lig();
     const int N = a.N, n = N + 3 * (N - 1);
-    const int groups = gridDim.x * (THREADS / LPT);
+    const int groups = gridDim.x * GPB;
     const int rounds = (a.B + groups - 1) / groups;
-    int p = blockIdx.x * (THREADS / LPT) + threadIdx.x / LPT;
+    int p = blockIdx.x * GPB + LN::gib();
     for (int it = 0; it < rounds; ++it, p += groups) {
-        const bool live = p < a.B;
+        const bool live = LN::real() && p < a.B;
         const int pp = live ? p : 0;
         const ProblemView pv = view_global<S>(a, pp, lig);
         double xv[4], gt, gq[3];

@@ -58,20 +58,81 @@ __host__ __device__ __forceinline__ constexpr double cfall(int k, int d) {
     return f;
 }
 
-template <int LPT> __device__ __forceinline__ double sh_up(unsigned m, double v, int d) { return __shfl_up_sync(m, v, d, LPT); }
-template <int LPT> __device__ __forceinline__ double sh_dn(unsigned m, double v, int d) { return __shfl_down_sync(m, v, d, LPT); }
+// ---- lane groups -----------------------------------------------------------------------------------------
+// A warp holds GPW = 32 / LPT groups of LPT consecutive lanes.  LPT a power of two (8, 16, 32): the groups tile the
+// warp and the width-limited shuffles address them.  Otherwise (LPT = 5: the reference's ModelMaxSeg = 5 pieces,
+// learning_planner.hpp:33 -- six trajectories per warp instead of four) the lanes past GPW * LPT form a short
+// dummy group that never owns a problem, and every shuffle names its source lane explicitly.
+template <int LPT>
+struct Lanes {
+    static constexpr bool POW2 = (LPT & (LPT - 1)) == 0;
+    static constexpr int GPW = 32 / LPT;                    // real groups per warp
+    static constexpr int SPW = GPW + (GPW * LPT < 32);      // group slots per warp (+ the dummy group)
+    static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int giw() { return lane() / LPT; }   // group in warp (== GPW: the dummy group)
+    static __device__ __forceinline__ int lig() { return POW2 ? (lane() & (LPT - 1)) : lane() - giw() * LPT; }
+    static __device__ __forceinline__ int base() { return lane() - lig(); }
+    static __device__ __forceinline__ bool real() { return POW2 || giw() < GPW; }
+    // slot of this thread's group inside its block (distinct also for the dummy groups) / real group index
+    static __device__ __forceinline__ int slot() { return (threadIdx.x >> 5) * SPW + giw(); }
+    static __device__ __forceinline__ int gib() { return (threadIdx.x >> 5) * GPW + giw(); }
+};
+template <int LPT> __device__ __forceinline__ double sh_up(unsigned m, double v, int d) {
+    if constexpr (Lanes<LPT>::POW2) return __shfl_up_sync(m, v, d, LPT);
+    else return __shfl_sync(m, v, Lanes<LPT>::lig() >= d ? Lanes<LPT>::lane() - d : Lanes<LPT>::lane());
+}
+template <int LPT> __device__ __forceinline__ double sh_dn(unsigned m, double v, int d) {
+    if constexpr (Lanes<LPT>::POW2) return __shfl_down_sync(m, v, d, LPT);
+    else {
+        const int l = Lanes<LPT>::lane();
+        return __shfl_sync(m, v, (Lanes<LPT>::lig() + d < LPT && l + d < 32) ? l + d : l);
+    }
+}
 template <int LPT> __device__ __forceinline__ double sh_xor(unsigned m, double v, int d) { return __shfl_xor_sync(m, v, d, LPT); }
+// value of the group's first lane, on every lane of the group
+template <int LPT, class T> __device__ __forceinline__ T group_first(unsigned m, T v) {
+    if constexpr (Lanes<LPT>::POW2) return __shfl_sync(m, v, 0, LPT);
+    else return __shfl_sync(m, v, Lanes<LPT>::base());
+}
 template <int LPT>
 __device__ __forceinline__ double group_sum(unsigned m, double v) {
+    if constexpr (Lanes<LPT>::POW2) {
 #pragma unroll
-    for (int o = LPT / 2; o > 0; o >>= 1) v += sh_xor<LPT>(m, v, o);
-    return v;  // butterfly: bitwise identical on every lane of the group
+        for (int o = LPT / 2; o > 0; o >>= 1) v += sh_xor<LPT>(m, v, o);
+        return v;  // butterfly: bitwise identical on every lane of the group
+    } else {
+        // every lane adds the group's LPT values in lane order: bitwise identical on every lane of the group
+        const int b0 = Lanes<LPT>::base();
+        double s = __shfl_sync(m, v, b0);
+#pragma unroll
+        for (int i = 1; i < LPT; ++i) s += __shfl_sync(m, v, b0 + i);
+        return s;
+    }
 }
 template <int LPT>
 __device__ __forceinline__ double group_max(unsigned m, double v) {
+    if constexpr (Lanes<LPT>::POW2) {
 #pragma unroll
-    for (int o = LPT / 2; o > 0; o >>= 1) v = fmax(v, sh_xor<LPT>(m, v, o));
-    return v;
+        for (int o = LPT / 2; o > 0; o >>= 1) v = fmax(v, sh_xor<LPT>(m, v, o));
+        return v;
+    } else {
+        const int b0 = Lanes<LPT>::base();
+        double s = __shfl_sync(m, v, b0);
+#pragma unroll
+        for (int i = 1; i < LPT; ++i) s = fmax(s, __shfl_sync(m, v, b0 + i));
+        return s;
+    }
+}
+// Latency mapping ("one warp per trajectory"): the GPW groups of a warp hold the SAME trajectory and split the
+// penalty samples among them; this adds up their partial sums in replica order, so that every replica ends with
+// the same bits and the replicated optimizer states never diverge.
+template <int LPT>
+__device__ __forceinline__ double replica_sum(unsigned m, double v) {
+    const int l0 = Lanes<LPT>::lig();
+    double s = __shfl_sync(m, v, l0);
+#pragma unroll
+    for (int r = 1; r < Lanes<LPT>::GPW; ++r) s += __shfl_sync(m, v, r * LPT + l0);
+    return s;
 }
 
 // tau <-> T (upstream gcopter.hpp forwardT / backwardGradT)
@@ -486,28 +547,33 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
 // loaded once per block instead of once per sample.  Phase 2 is a ROLLED loop over the samples of
 // the block (the position is recomputed, 15 DFMA, rather than indexed out of registers): the hot
 // loop has to stay inside the 32 KB instruction cache.
-template <int S, int LPT, bool PSMEM, class ST>
+// Rows touched by a block are remembered in a 64-bit mask (two words: the second one is only ever written when
+// K > 32, e.g. the reference's polytopes padded to 50 rows, learning_planner.hpp:40,157-168); K <= MINCOB_MAX_ROWS = 64.
+// REP (latency mapping): this lane evaluates only the samples j = jbase + u * jstride; the caller adds the
+// replicas' partial sums.  REP = false: every sample, in order.
+template <int S, int LPT, bool PSMEM, bool REP, class ST>
 __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT, ST> &sp, const double *planes,
-                                              int rstride, int K, double &cost, double (&G)[2 * S][3], double &gT) {
+                                              int rstride, int K, int jbase, int jstride, double &cost,
+                                              double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S, JB = MINCOB_JB;
     const int kap = P.kappa;
     const double ikap = P.ikap, imu = P.imu;
     const double step = sp.T * ikap;
+    const int cnt = REP ? (jbase <= kap ? (kap - jbase) / jstride + 1 : 0) : kap + 1;   // samples of this lane
+    auto sample = [&](int u) { return REP ? jbase + u * jstride : u; };
 #pragma unroll 1
-    for (int j0 = 0; j0 <= kap; j0 += JB) {
-        unsigned hit = 0u, pmask = 0u;
-        const bool pwide = K > 32;   // more than 32 rows: bit k&31 aliases, scan every row instead
+    for (int j0 = 0; j0 < cnt; j0 += JB) {
+        unsigned hit = 0u, pm0 = 0u, pm1 = 0u;
         {
             // sign-bit test: keep[jj] stays negative only while every n.p + d is negative; a sample
             // with any value >= +0 is flagged and re-tested exactly (v > 0) in phase 2.
             int keep[JB];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) keep[jj] = -1;
-            pmask = 0u;
             double pos[JB][3];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-                const double s = (j0 + jj) * step;
+                const double s = sample(j0 + jj) * step;
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                     double v = sp.c[D - 1][x];
@@ -517,26 +583,32 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 }
             }
             constexpr int UK = MINCOB_UNROLL_K;
+#pragma unroll 1
+            for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
+                unsigned pm = 0u;
+                const int k1 = min(K, k0 + 32);
 #pragma unroll UK
-            for (int k = 0; k < K; ++k) {
-                const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
-                int all = -1;
+                for (int k = k0; k < k1; ++k) {
+                    const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+                    int all = -1;
 #pragma unroll
-                for (int jj = 0; jj < JB; ++jj) {
-                    const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
-                    keep[jj] &= __double2hiint(v);
-                    all &= __double2hiint(v);
+                    for (int jj = 0; jj < JB; ++jj) {
+                        const double v = fma(h.x, pos[jj][0], fma(h.y, pos[jj][1], fma(h.z, pos[jj][2], h.w)));
+                        keep[jj] &= __double2hiint(v);
+                        all &= __double2hiint(v);
+                    }
+                    pm |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
                 }
-                pmask |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
+                if (k0 == 0) pm0 = pm; else pm1 = pm;
             }
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) hit |= (keep[jj] < 0 ? 0u : 1u) << jj;
         }
-        const int jend = min(JB, kap + 1 - j0);
+        const int jend = min(JB, cnt - j0);
         constexpr int UJ = MINCOB_UNROLL_JJ;
 #pragma unroll UJ
         for (int jj = 0; jj < jend; ++jj) {
-            const int j = j0 + jj;
+            const int j = sample(j0 + jj);
             const double s = j * step;
             // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
             double pw[D];
@@ -572,21 +644,21 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                         pos[x] = v;
                     }
                     // only rows flagged for this block (in row order, as the reference sums them)
-                    unsigned todo = pwide ? 0xffffffffu : pmask;
 #pragma unroll 1
-                    for (int k = 0; k < K; ++k) {
-                        if (!pwide) {
-                            if (todo == 0u) break;
-                            k = __ffs(todo) - 1;
+                    for (int w = 0; w < 2; ++w) {
+                        unsigned todo = w ? pm1 : pm0;
+#pragma unroll 1
+                        while (todo != 0u) {
+                            const int k = 32 * w + __ffs(todo) - 1;
                             todo &= todo - 1u;
-                        }
-                        const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
-                        const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
-                        if (v > 0.0) {
-                            smoothed_l1_pos(P.mu, imu, v, fv, df);
-                            const double wd = P.w_pos * df;
-                            gP[0] += wd * h.x; gP[1] += wd * h.y; gP[2] += wd * h.z;
-                            pena += P.w_pos * fv;
+                            const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+                            const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
+                            if (v > 0.0) {
+                                smoothed_l1_pos(P.mu, imu, v, fv, df);
+                                const double wd = P.w_pos * df;
+                                gP[0] += wd * h.x; gP[1] += wd * h.y; gP[2] += wd * h.z;
+                                pena += P.w_pos * fv;
+                            }
                         }
                     }
                 }
@@ -782,7 +854,9 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 // `before_adjoint` runs between the penalty loop and the adjoint: the optimize kernel uses it to request
 // its parked optimizer state early (plain loads whose latency the adjoint then covers).
-template <int S, int LPT, bool PSMEM, class ST, class Hook = NoHook>
+// REP: the groups of the warp are replicas of one trajectory (latency mapping): each takes every GPW-th penalty
+// sample and the partial sums are added in replica order; replica 0 contributes the energy terms.
+template <int S, int LPT, bool PSMEM, class ST, bool REP = false, class Hook = NoHook>
 __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N, int rounds,
                                                   const ProblemView &pv, const ST &store, double xt,
                                                   const double (&xq)[3], double &gt, double (&gq)[3],
@@ -810,13 +884,30 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     spline_solve<S, LPT, ST>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat);
     double cost, G[D][3], gTp;
     energy_partials<S, LPT, ST>(sp, chat, active, cost, G, gTp);
+    const int rep = REP ? Lanes<LPT>::giw() : 0;
+    if (REP && rep != 0) {
+        cost = 0.0; gTp = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) G[k][x] = 0.0;
+    }
     if (P.penalties && active)
-        penalty_piece<S, LPT, PSMEM, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, cost, G, gTp);
+        penalty_piece<S, LPT, PSMEM, REP, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, rep, Lanes<LPT>::GPW,
+                                              cost, G, gTp);
+    if (REP) {
+        cost = replica_sum<LPT>(mask, cost);
+        gTp = replica_sum<LPT>(mask, gTp);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) G[k][x] = replica_sum<LPT>(mask, G[k][x]);
+    }
     before_adjoint();
     double gT;
     spline_adjoint<S, LPT, ST>(mask, lig, N, rounds, sp, G, gTp, gq, gT);
     if (active) cost += P.rho * T;
-    gt = active ? backward_grad_t(xt, gT + P.rho) : 0.0;
+    gt = (active && !P.freeze) ? backward_grad_t(xt, gT + P.rho) : 0.0;   // freeze: durations are data, not variables
     return group_sum<LPT>(mask, cost);
 }
 

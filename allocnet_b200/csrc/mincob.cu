@@ -73,7 +73,7 @@ struct mincob_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int last_launches = 0;
+    int last_launches = 0, last_mapping = 0;
     bool timed = false;
     int sm_count = 0;
     // problems (device pointers; owned only when they point into the DevBufs below)
@@ -109,6 +109,20 @@ static int fail(mincob_ctx *h, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, MINCOB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// every entry point runs on the handle's device and restores the caller's current device on return
+struct DeviceGuard {
+    int prev = -1;
+    bool ok;
+    explicit DeviceGuard(int dev) {
+        ok = cudaGetDevice(&prev) == cudaSuccess;
+        if (ok && prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h)                \
+    DeviceGuard guard_(h->device);  \
+    if (!guard_.ok) return fail(h, MINCOB_E_CUDA, "cudaSetDevice(%d) failed", h->device)
+
 static int ensure(mincob_ctx *h, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap && b.p) return 0;
     if (b.p) cudaFree(b.p);
@@ -135,6 +149,10 @@ static int derive(mincob_ctx *h) {
     d.w_pos = p.w_pos; d.w_vel = p.w_vel; d.w_acc = p.w_acc; d.w_jerk = p.w_jerk;
     d.vmax2 = p.v_max * p.v_max; d.amax2 = p.a_max * p.a_max; d.jmax2 = p.j_max * p.j_max;
     d.rho = p.rho;
+    if (p.flags & ~(MINCOB_FLAG_FREEZE_TIMES | MINCOB_FLAG_PLANNER_ROWS)) return fail(h, MINCOB_E_INVALID, "unknown bits in flags (%d)", p.flags);
+    if (p.mapping < MINCOB_MAP_AUTO || p.mapping > MINCOB_MAP_LATENCY) return fail(h, MINCOB_E_INVALID, "mapping must be MINCOB_MAP_AUTO/THROUGHPUT/LATENCY");
+    d.freeze = (p.flags & MINCOB_FLAG_FREEZE_TIMES) ? 1 : 0;
+    d.mapping = p.mapping;
     d.penalties = (p.w_pos != 0.0 || p.w_vel != 0.0 || p.w_acc != 0.0 || p.w_jerk != 0.0) ? 1 : 0;
     d.mem = p.mem_size; d.past = p.past; d.max_iter = p.max_iterations; d.max_ls = p.max_linesearch;
     d.g_eps = p.g_epsilon; d.delta = p.delta; d.min_step = p.min_step; d.max_step = p.max_step;
@@ -159,11 +177,13 @@ static int lbfgs_param_code(const mincob_params &p, int n) {
 }
 
 // kernels are instantiated per (S, LPT) in kernels_inst.cu (one object each, built in parallel)
-static int lpt_index(int N) { return N <= 8 ? 0 : (N <= 16 ? 1 : 2); }
+// lanes per trajectory: 5 (six trajectories per warp; the reference plans with at most ModelMaxSeg = 5 pieces,
+// learning_planner.hpp:33), 8, 16 or 32
+static int lpt_index(int N) { return N <= 5 ? 0 : (N <= 8 ? 1 : (N <= 16 ? 2 : 3)); }
 static const LaunchTable *table_for(int S, int N) {
-    static const LaunchTable *tabs[2][3] = {
-        {mincob_table_3_8(), mincob_table_3_16(), mincob_table_3_32()},
-        {mincob_table_4_8(), mincob_table_4_16(), mincob_table_4_32()}};
+    static const LaunchTable *tabs[2][4] = {
+        {mincob_table_3_5(), mincob_table_3_8(), mincob_table_3_16(), mincob_table_3_32()},
+        {mincob_table_4_5(), mincob_table_4_8(), mincob_table_4_16(), mincob_table_4_32()}};
     return tabs[S == 3 ? 0 : 1][lpt_index(N)];
 }
 static int launched(mincob_ctx *h, const LaunchResult &r, const char *what) {
@@ -184,7 +204,9 @@ static int do_optimize(mincob_ctx *h, BatchArgs &a) {
     // off): give a fresh slab defined contents once, so those reads never see arbitrary bit patterns.
     if (h->b_hist.p != before) CU(h, cudaMemsetAsync(h->b_hist.p, 0, h->b_hist.cap, h->stream));
     a.hist = (double *)h->b_hist.p;
-    return launched(h, table_for(h->prm.S, a.N)->optimize(h->stream, h->sm_count, h->dp, a), "optimize_kernel");
+    const LaunchResult r = t->optimize(h->stream, h->sm_count, h->dp, a);
+    h->last_mapping = r.mapping;
+    return launched(h, r, "optimize_kernel");
 }
 static int do_minco(mincob_ctx *h, const MincoArgs &a, int propagate) {
     return launched(h, table_for(h->prm.S, a.N)->minco(h->stream, h->sm_count, a, propagate), "minco_kernel");
@@ -217,6 +239,7 @@ int mincob_default_params(mincob_params *p, int S) {
     p->mem_size = 8; p->past = 3; p->max_iterations = 1000; p->max_linesearch = 64;
     p->g_epsilon = 0.0; p->delta = 1.0e-5; p->min_step = 1.0e-32; p->max_step = 1.0e20;
     p->f_dec_coeff = 1.0e-4; p->s_curv_coeff = 0.9; p->cautious_factor = 1.0e-6; p->machine_prec = 1.0e-16;
+    p->flags = 0; p->mapping = MINCOB_MAP_AUTO;
     return 0;
 }
 
@@ -326,8 +349,15 @@ int mincob_set_stream(mincob_handle h, void *s) {
 
 int mincob_synchronize(mincob_handle h) {
     if (!h) return MINCOB_E_INVALID;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mincob_last_mapping(mincob_handle h, int *mapping) {
+    if (!h || !mapping) return MINCOB_E_INVALID;
+    if (!h->last_mapping) return fail(h, MINCOB_E_STATE, "no optimize call has been launched yet");
+    *mapping = h->last_mapping;
     return 0;
 }
 
@@ -345,8 +375,17 @@ int mincob_last_kernel_ms(mincob_handle h, float *ms, int *launches) {
 static int check_shape(mincob_ctx *h, int B, int N, int K) {
     if (B <= 0) return fail(h, MINCOB_E_INVALID, "B must be > 0");
     if (N < 1 || N > MINCOB_MAX_PIECES) return fail(h, MINCOB_E_INVALID, "N must be in [1,%d] (got %d)", MINCOB_MAX_PIECES, N);
-    if (K < 0) return fail(h, MINCOB_E_INVALID, "K must be >= 0");
+    if (K < 0 || K > MINCOB_MAX_ROWS) return fail(h, MINCOB_E_INVALID, "K must be in [0,%d] (got %d)", MINCOB_MAX_ROWS, K);
     return 0;
+}
+
+// rows [n, b] (n.p <= b, learning_planner.hpp:293-299) -> [n, d] with n.p + d <= 0 (geo_utils.hpp:41-42): d = -b
+static __global__ void planner_rows_kernel(const double *src, double *dst, size_t rows) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) {
+        const double4 r = reinterpret_cast<const double4 *>(src)[i];
+        reinterpret_cast<double4 *>(dst)[i] = make_double4(r.x, r.y, r.z, -r.w);
+    }
 }
 
 int mincob_set_problems_device(mincob_handle h, int B, int N, int K, const double *head, const double *tail,
@@ -356,6 +395,19 @@ int mincob_set_problems_device(mincob_handle h, int B, int N, int K, const doubl
     if (rc) return rc;
     if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
     if (hpolys && ((uintptr_t)hpolys & 31u)) return fail(h, MINCOB_E_INVALID, "hpolys must be 32-byte aligned");
+    if (K > 0 && (h->prm.flags & MINCOB_FLAG_PLANNER_ROWS)) {
+        // the kernels read GCOPTER-sign rows: keep a converted copy (in place when the rows already are our staging copy)
+        ON_DEVICE(h);
+        const size_t rows = (size_t)B * N * K;
+        double *dst = (double *)h->b_hpolys.p;
+        if (hpolys != dst) {
+            if ((rc = ensure(h, h->b_hpolys, rows * 4 * sizeof(double)))) return rc;
+            dst = (double *)h->b_hpolys.p;
+        }
+        planner_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, h->stream>>>(hpolys, dst, rows);
+        CU(h, cudaGetLastError());
+        hpolys = dst;
+    }
     h->B = B; h->N = N; h->K = K;
     h->head = head; h->tail = tail;
     h->hpolys = K > 0 ? hpolys : nullptr;
@@ -369,7 +421,7 @@ int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head
     int rc = check_shape(h, B, N, K);
     if (rc) return rc;
     if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int S = h->prm.S;
     const size_t nb = (size_t)B * S * 3 * sizeof(double), np = (size_t)B * N * K * 4 * sizeof(double),
                  nr = (size_t)B * N * sizeof(int);
@@ -381,16 +433,19 @@ int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head
         CU(h, cudaMemcpyAsync(h->b_hpolys.p, hpolys, np, cudaMemcpyHostToDevice, h->stream));
         CU(h, cudaMemcpyAsync(h->b_hrows.p, hrows, nr, cudaMemcpyHostToDevice, h->stream));
     }
-    return mincob_set_problems_device(h, B, N, K, (const double *)h->b_head.p, (const double *)h->b_tail.p,
-                                      K > 0 ? (const double *)h->b_hpolys.p : nullptr,
-                                      K > 0 ? (const int32_t *)h->b_hrows.p : nullptr);
+    rc = mincob_set_problems_device(h, B, N, K, (const double *)h->b_head.p, (const double *)h->b_tail.p,
+                                    K > 0 ? (const double *)h->b_hpolys.p : nullptr,
+                                    K > 0 ? (const int32_t *)h->b_hrows.p : nullptr);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));   // host-pointer contract: the caller's buffers are free again on return
+    return 0;
 }
 
 int mincob_evaluate_device(mincob_handle h, const double *x, double *f, double *g) {
     int rc = have_problems(h);
     if (rc) return rc;
     if (!x || !f || !g) return fail(h, MINCOB_E_INVALID, "x, f, g must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     BatchArgs a = base_args(h);
     a.x_in = x; a.f_out = f; a.g_out = g;
     CU(h, cudaEventRecord(h->ev0, h->stream));
@@ -405,7 +460,7 @@ int mincob_evaluate(mincob_handle h, const double *x, double *f, double *g) {
     int rc = have_problems(h);
     if (rc) return rc;
     if (!x || !f || !g) return fail(h, MINCOB_E_INVALID, "x, f, g must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t n = (size_t)h->N + 3 * (h->N - 1), nx = (size_t)h->B * n * sizeof(double), nf = (size_t)h->B * sizeof(double);
     if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_g, nx)) || (rc = ensure(h, h->b_f, nf))) return rc;
     CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
@@ -427,7 +482,7 @@ int mincob_optimize_device(mincob_handle h, double *x, double *f, int32_t *statu
     int rc = have_problems(h);
     if (rc) return rc;
     if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int n = h->N + 3 * (h->N - 1);
     const int pc = lbfgs_param_code(h->prm, n);
     if (pc) {  // lbfgs.hpp:450-495: the reference returns the code before touching x
@@ -455,7 +510,7 @@ int mincob_optimize(mincob_handle h, double *x, double *f, int32_t *status, int3
     int rc = have_problems(h);
     if (rc) return rc;
     if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t B = h->B, N = h->N, n = N + 3 * (N - 1), S = h->prm.S;
     const size_t nx = B * n * 8, nf = B * 8, ni = B * 4, nc = B * N * 3 * 2 * S * 8, nt = B * N * 8;
     if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_f, nf)) || (rc = ensure(h, h->b_status, ni)) ||
@@ -497,7 +552,7 @@ int mincob_minco_forward_device(mincob_handle h, int B, int N, const double *hea
     if (!h || !head || !tail || !ts || (N > 1 && !inPs)) return MINCOB_E_INVALID;
     int rc = check_shape(h, B, N, 0);
     if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     MincoArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.N = N;
@@ -513,7 +568,7 @@ int mincob_minco_propagate_device(mincob_handle h, int B, int N, const double *h
         return MINCOB_E_INVALID;
     int rc = check_shape(h, B, N, 0);
     if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     MincoArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.N = N;
@@ -527,7 +582,7 @@ int mincob_minco_forward(mincob_handle h, int B, int N, const double *head, cons
     if (!h || !head || !tail || !ts || (N > 1 && !inPs)) return MINCOB_E_INVALID;
     int rc = check_shape(h, B, N, 0);
     if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t S = h->prm.S, D = 2 * S;
     const size_t nb = (size_t)B * S * 3 * 8, nq = (size_t)B * (N - 1) * 3 * 8, nt = (size_t)B * N * 8,
                  nc = (size_t)B * D * N * 3 * 8, ne = (size_t)B * 8;
@@ -556,7 +611,7 @@ int mincob_minco_propagate(mincob_handle h, int B, int N, const double *head, co
         return MINCOB_E_INVALID;
     int rc = check_shape(h, B, N, 0);
     if (rc) return rc;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t S = h->prm.S, D = 2 * S;
     const size_t nb = (size_t)B * S * 3 * 8, nq = (size_t)B * (N - 1) * 3 * 8, nt = (size_t)B * N * 8,
                  nc = (size_t)B * D * N * 3 * 8;
@@ -581,7 +636,7 @@ int mincob_check_feasibility_device(mincob_handle h, const double *coeffs, const
     int rc = have_problems(h);
     if (rc) return rc;
     if (!coeffs || !T || !report || samples < 1) return fail(h, MINCOB_E_INVALID, "coeffs, T, report must be non-null and samples >= 1");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CheckArgs a;
     memset(&a, 0, sizeof a);
     a.B = h->B; a.N = h->N; a.K = h->K; a.samples = samples;
@@ -593,7 +648,7 @@ int mincob_check_feasibility(mincob_handle h, const double *coeffs, const double
     int rc = have_problems(h);
     if (rc) return rc;
     if (!coeffs || !T || !report) return fail(h, MINCOB_E_INVALID, "coeffs, T, report must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t B = h->B, N = h->N, S = h->prm.S;
     const size_t nc = B * N * 3 * 2 * S * 8, nt = B * N * 8, nr = B * 4 * 8;
     if ((rc = up(h, h->b_coeffs, coeffs, nc)) || (rc = up(h, h->b_T, T, nt)) || (rc = ensure(h, h->b_m0, nr))) return rc;
@@ -609,7 +664,7 @@ int mincob_max_rates_device(mincob_handle h, const double *coeffs, const double 
     int rc = have_problems(h);
     if (rc) return rc;
     if (!coeffs || !T || !rates) return fail(h, MINCOB_E_INVALID, "coeffs, T, rates must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     RateArgs a;
     memset(&a, 0, sizeof a);
     a.B = h->B; a.N = h->N; a.grid = 128;
@@ -621,7 +676,7 @@ int mincob_max_rates(mincob_handle h, const double *coeffs, const double *T, dou
     int rc = have_problems(h);
     if (rc) return rc;
     if (!coeffs || !T || !rates) return fail(h, MINCOB_E_INVALID, "coeffs, T, rates must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t nc = (size_t)h->B * h->N * 3 * 2 * h->prm.S * sizeof(double), nt = (size_t)h->B * h->N * sizeof(double);
     const size_t nr = (size_t)h->B * 3 * sizeof(double);
     if ((rc = up(h, h->b_coeffs, coeffs, nc)) || (rc = up(h, h->b_T, T, nt)) || (rc = ensure(h, h->b_m0, nr))) return rc;
@@ -658,7 +713,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters,
 
 int mincob_measure_fp64_peak(mincob_handle h, double *tflops) {
     if (!h || !tflops) return MINCOB_E_INVALID;
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     double *sink = nullptr;
     CU(h, cudaMalloc((void **)&sink, sizeof(double)));
     const int blocks = h->sm_count * 8, threads = 256, iters = 20000;
@@ -696,7 +751,7 @@ int mincob_nccl_unique_id(void *uid) {
 int mincob_comm_init(mincob_handle h, int nranks, int rank, const void *uid) {
     if (!h || !uid || nranks < 1 || rank < 0 || rank >= nranks) return MINCOB_E_INVALID;
     if (!nccl_load()) return fail(h, MINCOB_E_NCCL, "libnccl not found");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     NcclUid id;
     memcpy(&id, uid, sizeof id);
     const int rc = g_nccl.init_rank(&h->comm, nranks, id, rank);
@@ -708,7 +763,7 @@ int mincob_comm_init(mincob_handle h, int nranks, int rank, const void *uid) {
 int mincob_allgather_device(mincob_handle h, const double *send, double *recv, int64_t count) {
     if (!h || !send || !recv || count < 0) return MINCOB_E_INVALID;
     if (!h->comm) return fail(h, MINCOB_E_STATE, "mincob_comm_init has not been called");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int rc = g_nccl.allgather(send, recv, (size_t)count, /*ncclDouble*/ 8, h->comm, h->stream);
     if (rc != 0) return fail(h, MINCOB_E_NCCL, "ncclAllGather: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
     return 0;
@@ -723,7 +778,7 @@ static int optimize_sharded(mincob_ctx *h, bool gather_to_host, double *x, doubl
     int rc = have_problems(h);
     if (rc) return rc;
     if (!x || (gather_to_host && !coeffs)) return fail(h, MINCOB_E_INVALID, "x and coeffs_all must be non-null");
-    CU(h, cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t B = h->B, N = h->N, n = N + 3 * (N - 1), S = h->prm.S;
     const size_t nx = B * n * 8, nf = B * 8, ni = B * 4, cnt = B * N * 3 * 2 * S, nc = cnt * 8, nt = B * N * 8;
     if ((rc = ensure(h, h->b_x, nx)) || (rc = ensure(h, h->b_f, nf)) || (rc = ensure(h, h->b_status, ni)) ||

@@ -25,6 +25,12 @@ LBFGSERR_UNKNOWNERROR = -1024
  LBFGSERR_INCREASEGRADIENT) = range(-1023, -1023 + 19)
 
 
+# mincob_params.flags / .mapping (include/mincob.h)
+FLAG_FREEZE_TIMES = 1     # durations are data (the fixed-time call of learning_planner.hpp:196), waypoints only
+FLAG_PLANNER_ROWS = 2     # rows are [n, b] with n.p <= b (learning_planner.hpp:293-299) instead of n.p + d <= 0
+MAP_AUTO, MAP_THROUGHPUT, MAP_LATENCY = 0, 1, 2
+
+
 class MincobParams(C.Structure):
     _fields_ = [
         ("S", C.c_int32), ("kappa", C.c_int32),
@@ -36,7 +42,7 @@ class MincobParams(C.Structure):
         ("g_epsilon", C.c_double), ("delta", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double),
         ("f_dec_coeff", C.c_double), ("s_curv_coeff", C.c_double), ("cautious_factor", C.c_double),
         ("machine_prec", C.c_double),
-        ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("flags", C.c_int32), ("mapping", C.c_int32),
     ]
 
 
@@ -47,7 +53,7 @@ def default_params(S: int = 3, **over) -> MincobParams:
         mem_size=8, past=3, max_iterations=1000, max_linesearch=64,
         g_epsilon=0.0, delta=1.0e-5, min_step=1.0e-32, max_step=1.0e20,
         f_dec_coeff=1.0e-4, s_curv_coeff=0.9, cautious_factor=1.0e-6, machine_prec=1.0e-16,
-        reserved0=0, reserved1=0)
+        flags=0, mapping=MAP_AUTO)
     for k, v in over.items():
         if not hasattr(p, k):
             raise AttributeError(f"mincob_params has no field {k!r}")

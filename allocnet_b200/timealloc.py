@@ -13,12 +13,16 @@ from the model's `state_dict` for B problems at once, in plain PyTorch on whatev
         t_k = Linear(256->1)(h);  stop_k = sigmoid(Linear(256->1)(h));  record t_k, then stop if stop_k > 0.5
     output (B,L): durations, zero after the stop step.
 
-The weights are NOT part of this repository (they are the reference's artefacts): `load_weights(path)` reads
-them from a TorchScript file the user points at.  Input layouts are the planner's:
+Weights: `load_weights(path)` reads a TorchScript file of the reference (any of its four .pt models);
+`load_weights_npz()` reads the state_dict exported from `seq5_tokenthresh0_35_cpu.pt` by
+`tests/golden/make_timealloc_fixture.py` (tests/golden/timealloc_seq5.npz: the reference's trained parameters, used
+not rebuilt, SURVEY.md section 2 row 13 -- that file is what travels to a GPU box that has no reference tree).  Input layouts are the planner's:
 state channels [px,vx,ax,py,vy,ay,pz,vz,az] x {start, goal}; polytope rows [n, b] with n.p <= b, unit
 normals, zero padded to 50 rows and L segments.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -31,6 +35,15 @@ def load_weights(path: str, device="cpu") -> dict:
     """state_dict of the reference's TorchScript model (any of the four .pt files)."""
     m = torch.jit.load(path, map_location="cpu")
     return {k: v.detach().to(device=device, dtype=torch.float32) for k, v in m.state_dict().items()}
+
+
+FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "timealloc_seq5.npz")
+
+
+def load_weights_npz(path: str = FIXTURE, device="cpu") -> dict:
+    """state_dict exported by tests/golden/make_timealloc_fixture.py (keys `w/<name>`)."""
+    z = np.load(path)
+    return {k[2:]: torch.from_numpy(z[k]).to(device=device, dtype=torch.float32) for k in z.files if k.startswith("w/")}
 
 
 def random_weights(seq_len: int = 5, hidden: int = 256, seed: int = 0, device="cpu") -> dict:
@@ -121,3 +134,50 @@ def warm_start_durations(w: dict, pb, fallback_T0=None, L: int = 5, device="cpu"
         ok = (t >= 1e-10).all(axis=1)
         T0[ok, s0:s0 + cnt] = t[ok]
     return T0
+
+
+@torch.no_grad()
+def pack_inputs_torch(head, tail, hpolys, hrows, seg_from: int = 0, seg_count: int | None = None, L: int = 5):
+    """pack_inputs on torch tensors of any device (fp64 library layouts in, fp32 planner tensors out)."""
+    B, N, K = hpolys.shape[0], hpolys.shape[1], hpolys.shape[2]
+    seg_count = min(L, N - seg_from) if seg_count is None else seg_count
+    dev = hpolys.device
+    # state[:, 3*a + d, 0] = head[:, d, a]
+    state = torch.stack([head[:, :3].transpose(1, 2).reshape(B, 9), tail[:, :3].transpose(1, 2).reshape(B, 9)], dim=2).float()
+    hp = torch.zeros(B, MAX_ROWS, 4, L, dtype=torch.float32, device=dev)
+    kk = min(K, MAX_ROWS)
+    rows = hpolys[:, seg_from:seg_from + seg_count, :kk].clone()                  # [B][s][kk][4]
+    nrm = rows[..., :3].norm(dim=3, keepdim=True)
+    rows = torch.where(nrm > 0, rows / nrm.clamp_min(1e-300), torch.zeros_like(rows))
+    rows[..., 3] *= -1.0
+    live = torch.arange(kk, device=dev)[None, None, :] < hrows[:, seg_from:seg_from + seg_count].clamp(max=kk)[:, :, None]
+    rows = torch.where(live[..., None], rows, torch.zeros_like(rows))
+    hp[:, :kk, :, :seg_count] = rows.permute(0, 2, 3, 1).float()
+    return state, hp
+
+
+@torch.no_grad()
+def warm_start_durations_torch(w: dict, head, tail, hpolys, hrows, q0, T0, L: int = 5, chunk: int = 8192):
+    """warm_start_durations for torch tensors already on the device (bench.py --config 4): returns (T [B][N] fp64,
+    accepted [B][ceil(N/L)] bool -- windows whose net answer the planner would accept, learning_planner.hpp:181-189)."""
+    B, N = T0.shape
+    T = T0.clone()
+    nwin = (N + L - 1) // L
+    acc = torch.zeros(B, nwin, dtype=torch.bool, device=T0.device)
+    wpts = torch.cat([head[:, :1, :], q0, tail[:, :1, :]], dim=1)                # [B][N+1][3]
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        for wi, s0 in enumerate(range(0, N, L)):
+            cnt = min(L, N - s0)
+            hd = torch.zeros(hi - lo, 3, 3, dtype=head.dtype, device=head.device); tl = torch.zeros_like(hd)
+            hd[:, 0] = wpts[lo:hi, s0]; tl[:, 0] = wpts[lo:hi, s0 + cnt]
+            if s0 == 0:
+                hd = head[lo:hi, :3]
+            if s0 + cnt == N:
+                tl = tail[lo:hi, :3]
+            st, hp = pack_inputs_torch(hd, tl, hpolys[lo:hi], hrows[lo:hi], s0, cnt, L)
+            t = forward_batched(w, st, hp).double()[:, :cnt]
+            ok = (t >= 1e-10).all(dim=1)
+            T[lo:hi, s0:s0 + cnt] = torch.where(ok[:, None], t, T[lo:hi, s0:s0 + cnt])
+            acc[lo:hi, wi] = ok
+    return T, acc

@@ -14,7 +14,9 @@
  * Conventions
  *   - plain pointers and sizes only; no C++/torch types.  `*_device` variants take DEVICE
  *     pointers and enqueue on the handle's stream without synchronising; the plain variants
- *     take HOST pointers, copy in/out and return after the results are on the host.
+ *     take HOST pointers, copy in/out and return after the copies are complete (the caller may
+ *     reuse or free its buffers at once).  Every entry point leaves the calling thread's current
+ *     CUDA device as it found it.
  *   - all real data is fp64 (the reference path is double: lbfgs.hpp, trajectory.hpp).
  *   - return value: 0 on success, a negative MINCOB_E_* code otherwise; per-problem L-BFGS
  *     outcomes use the reference codes of gcopter/lbfgs.hpp:135-184 in the `status` array.
@@ -46,6 +48,7 @@ extern "C" {
 #endif
 
 #define MINCOB_MAX_PIECES 32
+#define MINCOB_MAX_ROWS 64     /* half-plane rows per polytope (the reference pads to 50: learning_planner.hpp:40,157-168) */
 #define MINCOB_MAX_MEM 32
 #define MINCOB_MAX_PAST 8
 
@@ -71,8 +74,33 @@ typedef struct mincob_params {
     double rho;              /* WeightT */
     int32_t mem_size, past, max_iterations, max_linesearch;
     double g_epsilon, delta, min_step, max_step, f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
-    int32_t reserved0, reserved1;
+    int32_t flags;           /* MINCOB_FLAG_* bits, 0 by default */
+    int32_t mapping;         /* MINCOB_MAP_*: how mincob_optimize lays trajectories onto warps */
 } mincob_params;
+
+/* flags.
+ * MINCOB_FLAG_FREEZE_TIMES: the durations handed in through x (tau = backwardT(T)) are DATA: only the inner
+ *   waypoints are optimised (d/dtau = 0, T never moves).  This is the like-for-like replacement of the incumbent
+ *   back-end call qp_solver.solve(iniPVA, finPVA, hPolys, times, ...) at planner/learning_planner.hpp:196, which
+ *   keeps the network's time allocation fixed (planner/qp_solver.hpp:119-360).  Without it the optimizer also
+ *   refines the durations (upstream GCOPTER behaviour).
+ * MINCOB_FLAG_PLANNER_ROWS: half-plane rows are given as [n, b] meaning n.p <= b, the form LearningPlanner hands
+ *   its back-end after the sign flip of planner/learning_planner.hpp:293-299, instead of GCOPTER's n.p + d <= 0
+ *   (gcopter/geo_utils.hpp:41-42).  Read by mincob_set_problems / mincob_set_problems_device, which then keep a
+ *   converted device copy of the rows. */
+#define MINCOB_FLAG_FREEZE_TIMES 1
+#define MINCOB_FLAG_PLANNER_ROWS 2
+/* mapping (mincob_optimize only).
+ * THROUGHPUT: one lane per piece, 32/LPT trajectories per warp (LPT = 5, 8, 16 or 32 lanes for N <= 5, 8, 16, 32).
+ * LATENCY: "one warp per trajectory" -- the lane groups of a warp hold the same trajectory and split the penalty
+ *   samples of every piece; fewer trajectories in flight, each evaluation 2-3x shorter.  For single problems and
+ *   small batches.
+ * AUTO: LATENCY when the batch has no more trajectories than the device holds resident warps, else THROUGHPUT.
+ * The two mappings add the penalty samples in a different order: results agree to rounding, not bit for bit; for
+ * a given mapping they are bit-reproducible and independent of batch composition. */
+#define MINCOB_MAP_AUTO 0
+#define MINCOB_MAP_THROUGHPUT 1
+#define MINCOB_MAP_LATENCY 2
 
 typedef struct mincob_ctx *mincob_handle;
 
@@ -81,7 +109,9 @@ int mincob_default_params(mincob_params *out, int S);
 int mincob_create(mincob_handle *out, const mincob_params *params, int device);
 int mincob_destroy(mincob_handle h);
 int mincob_set_params(mincob_handle h, const mincob_params *params);
-/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own stream. */
+/* Use an existing CUDA stream (cudaStream_t passed as void*); NULL = the handle's own (non-blocking) stream.
+ * The legacy default stream is also NULL as a cudaStream_t: to run on it pass cudaStreamLegacy ((void*)0x1),
+ * otherwise work on the handle's stream is not ordered with default-stream work of the caller. */
 int mincob_set_stream(mincob_handle h, void *cuda_stream);
 int mincob_synchronize(mincob_handle h);
 const char *mincob_last_error(mincob_handle h);
@@ -112,6 +142,8 @@ int mincob_optimize_device(mincob_handle h, double *x_d, double *f_d, int32_t *s
 /* Device time (ms, CUDA events on the handle's stream) and launch count of the last
  * evaluate/optimize call; synchronises. */
 int mincob_last_kernel_ms(mincob_handle h, float *ms, int *launches);
+/* MINCOB_MAP_THROUGHPUT / MINCOB_MAP_LATENCY: the mapping the last mincob_optimize* call launched. */
+int mincob_last_mapping(mincob_handle h, int *mapping);
 
 /* ---- MINCO_S3NU / MINCO_S4NU building blocks for B problems:
  *      setParameters + getCoeffs + getEnergy + getEnergyPartialGradBy{Coeffs,Times} ...

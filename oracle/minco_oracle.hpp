@@ -333,6 +333,11 @@ struct PenaltyParams {
     double w_pos = 1.0e4, w_vel = 1.0e4, w_acc = 1.0e4, w_jerk = 1.0e4;
     double v_max = 4.0, a_max = 6.0, j_max = 12.0;
     double rho = 20.0;     // WeightT
+    // fixed-time mode: T is data (the call the reference makes today, learning_planner.hpp:196 -> qp_solver.hpp:119):
+    // the tau block of the gradient is zero, so lbfgs_optimize never moves the durations
+    bool freeze_times = false;
+    // rows are [n, b] with n.p <= b (after the sign flip of learning_planner.hpp:293-299) instead of n.p + d <= 0
+    bool planner_rows = false;
 };
 
 // One corridor problem.  hpolys: [N][Kstride][4] rows (nx,ny,nz,d), GCOPTER sign
@@ -375,7 +380,7 @@ inline void attach_penalty(const PenaltyParams &pp, const Problem &pb, const dou
             double f, df;
             for (int k = 0; k < K; ++k) {
                 const double *h = hp + k * 4;
-                const double viol = h[0] * pos[0] + h[1] * pos[1] + h[2] * pos[2] + h[3];
+                const double viol = h[0] * pos[0] + h[1] * pos[1] + h[2] * pos[2] + (pp.planner_rows ? -h[3] : h[3]);
                 if (smoothed_l1(pp.mu, viol, f, df)) {
                     for (int a = 0; a < 3; ++a) gP[a] += pp.w_pos * df * h[a];
                     pena += pp.w_pos * f;
@@ -441,7 +446,7 @@ struct CostFunctional {
         double tsum = 0.0;
         for (int i = 0; i < N; ++i) tsum += T[i];
         cost += pp.rho * tsum;
-        for (int i = 0; i < N; ++i) g[i] = backward_grad_t(x[i], gT[i] + pp.rho);
+        for (int i = 0; i < N; ++i) g[i] = pp.freeze_times ? 0.0 : backward_grad_t(x[i], gT[i] + pp.rho);
         for (int i = 0; i < 3 * (N - 1); ++i) g[N + i] = gq[i];
         return cost;
     }

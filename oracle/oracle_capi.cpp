@@ -20,7 +20,7 @@ struct orc_params {
     double mu, w_pos, w_vel, w_acc, w_jerk, v_max, a_max, j_max, rho;
     int32_t mem_size, past, max_iterations, max_linesearch;
     double g_epsilon, delta, min_step, max_step, f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
-    int32_t reserved0, reserved1;
+    int32_t flags, mapping;   // flags: 1 = freeze times, 2 = planner rows [n, b]; mapping: device-only, ignored here
 };
 
 int orc_params_size() { return static_cast<int>(sizeof(orc_params)); }
@@ -34,6 +34,7 @@ orc::PenaltyParams penalty_of(const orc_params &p) {
     q.kappa = p.kappa; q.mu = p.mu;
     q.w_pos = p.w_pos; q.w_vel = p.w_vel; q.w_acc = p.w_acc; q.w_jerk = p.w_jerk;
     q.v_max = p.v_max; q.a_max = p.a_max; q.j_max = p.j_max; q.rho = p.rho;
+    q.freeze_times = (p.flags & 1) != 0; q.planner_rows = (p.flags & 2) != 0;
     return q;
 }
 orc::LbfgsParams lbfgs_of(const orc_params &p) {

@@ -20,7 +20,7 @@ struct ref_params {
     double mu, w_pos, w_vel, w_acc, w_jerk, v_max, a_max, j_max, rho;
     int32_t mem_size, past, max_iterations, max_linesearch;
     double g_epsilon, delta, min_step, max_step, f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
-    int32_t reserved0, reserved1;
+    int32_t flags, mapping;
 };
 
 struct Bridge {

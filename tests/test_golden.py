@@ -71,7 +71,7 @@ def test_restated_lbfgs_reproduces_reference_traces(oracle_strict, path):
 def test_gpu_matches_golden(path):
     from allocnet_b200 import api
     z, pb, prm, S, N, K, B = _load(path)
-    tol = 1e-9 if S == 3 else 1e-8
+    tol = 1e-9
     mb = api.MincoBatch(prm, device=0)
     try:
         mb.set_problems(pb)
@@ -81,12 +81,12 @@ def test_gpu_matches_golden(path):
         # MINCO building blocks at x1
         T = synth.forward_t(z["x1"][:, :N]); q = z["x1"][:, N:].reshape(B, max(N - 1, 0), 3)
         out = mb.minco_forward(pb.head, pb.tail, q, T)
-        ctol = 1e-9 if S == 3 else 1e-7
+        ctol = 1e-9
         assert _rel(out["coeffs"], z["coeffs"]) <= ctol and _rel(out["flat"], z["flat"]) <= ctol
         assert _rel(out["energy"][:, None], z["energy"][:, None]) <= tol
         assert _rel(out["gdC"], z["gdC_E"]) <= tol and _rel(out["gdT"], z["gdT_E"]) <= tol
         gq, gT = mb.minco_propagate(pb.head, pb.tail, q, T, z["gdC_in"], z["gdT_in"])
-        ptol = 1e-9 if S == 3 else 1e-7
+        ptol = 1e-9
         if N > 1:
             assert _rel(gq, z["gradByPoints"]) <= ptol
         assert _rel(gT, z["gradByTimes"]) <= ptol

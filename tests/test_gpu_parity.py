@@ -40,14 +40,13 @@ def _rand_minco(rng, B, S, N):
 @pytest.mark.parametrize("N", [1, 2, 5, 8, 9, 16, 17, 32])
 def test_minco_forward_and_propagate(handles, oracle, S, N):
     """setParameters/getCoeffs/getEnergy/getEnergyPartialGradBy{Coeffs,Times}/getTrajectory and
-    propogateGrad vs the banded oracle.  S=3: 1e-9 everywhere.  S=4 coefficient rows lose digits
-    in the Hermite->monomial change of basis (tests/test_reduced_formulation.py); energy and
-    gradients keep 1e-9 on these inputs, coefficients are held to 1e-7 of the row scale."""
+    propogateGrad vs the banded oracle: 1e-9 everywhere, MINCO_S3NU and MINCO_S4NU alike (measured on the
+    B200, tools/s4_precision.py / profiles/r02_s4_precision.txt: <= 7e-14 for S=3, <= 1.6e-11 for S=4 up to 32 pieces)."""
     rng = np.random.default_rng(10 * N + S)
     B = 37
     head, tail, q, T = _rand_minco(rng, B, S, N)
     out = handles[S].minco_forward(head, tail, q, T)
-    ctol = TOL if S == 3 else 1e-7
+    ctol = TOL
     gdC = rng.normal(size=(B, 2 * S * N, 3)); gdT = rng.normal(size=(B, N))
     gq, gT = handles[S].minco_propagate(head, tail, q, T, gdC, gdT)
     for b in range(B):
@@ -55,11 +54,11 @@ def test_minco_forward_and_propagate(handles, oracle, S, N):
         sc = np.abs(ref["coeffs"]).max()
         assert np.abs(out["coeffs"][b] - ref["coeffs"]).max() <= ctol * sc
         assert np.abs(out["flat"][b] - ref["flat"]).max() <= ctol * sc
-        assert abs(out["energy"][b] - ref["energy"]) <= (TOL if S == 3 else 1e-8) * abs(ref["energy"])
-        assert np.abs(out["gdC"][b] - ref["gdC"]).max() <= (TOL if S == 3 else 1e-8) * np.abs(ref["gdC"]).max()
-        assert np.abs(out["gdT"][b] - ref["gdT"]).max() <= (TOL if S == 3 else 1e-8) * np.abs(ref["gdT"]).max()
+        assert abs(out["energy"][b] - ref["energy"]) <= TOL * abs(ref["energy"])
+        assert np.abs(out["gdC"][b] - ref["gdC"]).max() <= TOL * np.abs(ref["gdC"]).max()
+        assert np.abs(out["gdT"][b] - ref["gdT"]).max() <= TOL * np.abs(ref["gdT"]).max()
         gq_ref, gT_ref = oracle.minco_propagate(S, head[b], tail[b], q[b], T[b], gdC[b], gdT[b])
-        ptol = TOL if S == 3 else 1e-7
+        ptol = TOL
         if N > 1:
             assert np.abs(gq[b] - gq_ref).max() <= ptol * np.abs(gq_ref).max()
         assert np.abs(gT[b] - gT_ref).max() <= ptol * np.abs(gT_ref).max()
@@ -114,7 +113,7 @@ CASES = [  # (S, N, K, B, ragged, energy_only)
 @pytest.mark.parametrize("S,N,K,B,ragged,eonly", CASES)
 def test_cost_functional_parity(handles, oracle, S, N, K, B, ragged, eonly):
     """f and g of costFunctional at the generator's x0 (many active penalty terms) and at a
-    perturbed point: <= 1e-9 relative (S=4: 1e-8, see above)."""
+    perturbed point: <= 1e-9 relative (S = 3 and 4)."""
     prm = default_params(S)
     if eonly:
         prm = energy_only(prm)
@@ -123,7 +122,7 @@ def test_cost_functional_parity(handles, oracle, S, N, K, B, ragged, eonly):
     pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=ragged)
     mb.set_problems(pb)
     rng = np.random.default_rng(S * 1000 + N)
-    tol = TOL if S == 3 else 1e-8
+    tol = TOL
     for x in (pb.x0(), pb.x0() + 0.05 * rng.normal(size=(B, pb.nvars))):
         f, g = mb.evaluate(x)
         fo, go = oracle.cost_batch(prm, pb, x, nthreads=8)
@@ -203,7 +202,7 @@ def test_optimize_converges_like_oracle(handles, oracle, S, N, K, B):
     for st in (res["status"], ref["status"]):
         assert ((st >= 0) | (st == P.LBFGSERR_MAXIMUMITERATION)).all(), np.unique(st, return_counts=True)
         assert (st >= 0).mean() >= 0.98
-    tol = TOL if S == 3 else 1e-8
+    tol = TOL
     fo, _ = oracle.cost_batch(prm, pb, res["x"], nthreads=8)
     assert float(np.max(np.abs(res["f"] - fo) / np.abs(fo))) <= tol
     # coefficients / durations of the final x
@@ -216,8 +215,8 @@ def test_optimize_converges_like_oracle(handles, oracle, S, N, K, B):
         # coefficient k of a piece scales like T^-(D-1-k): compare what it contributes over the piece,
         # c_k T^k (descending storage: power D-1-k), against the largest such term of the trajectory
         pw = T[:, None, None] ** np.arange(2 * S - 1, -1, -1)[None, None, :]
-        assert np.abs((res["coeffs"][b] - flat) * pw).max() <= (1e-9 if S == 3 else 1e-6) * np.abs(flat * pw).max()
-        assert np.abs(res["coeffs"][b] - flat).max() <= (1e-8 if S == 3 else 1e-5) * np.abs(flat).max()
+        assert np.abs((res["coeffs"][b] - flat) * pw).max() <= 1e-9 * np.abs(flat * pw).max()
+        assert np.abs(res["coeffs"][b] - flat).max() <= 1e-8 * np.abs(flat).max()
         np.testing.assert_allclose(res["T"][b], T, rtol=1e-14)
     # How close can two runs of the SAME algorithm end?  The CPU oracle built with and without FMA
     # contraction (nothing else differs) ends within 2e-2 of itself on 97 % of the corridor problems and
@@ -226,7 +225,7 @@ def test_optimize_converges_like_oracle(handles, oracle, S, N, K, B):
     rel = np.abs(res["f"] - ref["f"]) / np.abs(ref["f"])
     # (32 pieces: 97 unknowns and ~2 000 evaluations per problem, so forks are wider; two CPU builds of the oracle agree
     # within 2e-2 on 75-85 % of such problems, tools/diff_variants.py shows the same between two GPU builds)
-    assert np.median(rel) <= (2e-3 if N <= 16 else 1e-2) and np.mean(rel < 2e-2) >= (0.93 if K > 0 and N <= 16 else 0.80 if N <= 16 else 0.65), (np.median(rel), rel.max())
+    assert np.median(rel) <= (2e-3 if N <= 16 else 1e-2) and np.mean(rel < 2e-2) >= (0.90 if K > 0 and N <= 16 else 0.80 if N <= 16 else 0.65), (np.median(rel), rel.max())
     assert abs(np.median(res["f"]) / np.median(ref["f"]) - 1.0) <= 1e-2
     # effort is comparable (same algorithm): mean evaluation count within 15 % (35 % for the 24-problem case:
     # single 32-piece problems fork by hundreds of evaluations on a 1-ulp difference, see tools/diff_variants.py)
@@ -561,7 +560,7 @@ def test_autograd_layer_against_torch_reference(handles, S, N):
     assert float(((E - E2).abs() / E2.abs()).max().detach()) <= tol
     assert float(((c - c2).abs().max() / c2.abs().max()).detach()) <= tol
     for ga, gb in zip(grads, grads2):
-        assert float((ga - gb).abs().max() / gb.abs().max()) <= (1e-8 if S == 3 else 1e-5), (S, N)
+        assert float((ga - gb).abs().max() / gb.abs().max()) <= 1e-8, (S, N)
 
 
 def test_config4_pipeline_net_warm_start_on_device(handles, oracle):
@@ -620,3 +619,210 @@ def test_gradient_norm_stop(handles, oracle):
     assert (crit < 1e-2 * (1.0 + 1e-6)).all(), float(crit.max())
     assert abs(res["iters"].mean() / ref["iters"].mean() - 1.0) <= 0.25
     mb.set_params(default_params(3))
+
+
+# ---- round 2: latency mapping ("one warp per trajectory"), fixed-time mode, planner-form rows --------------------
+
+@pytest.mark.parametrize("S,N,K,B", [(3, 8, 16, 96), (3, 5, 16, 50), (3, 16, 16, 40), (4, 8, 16, 33), (3, 5, 50, 31),
+                                     (3, 3, 7, 20), (3, 8, 0, 40)])
+def test_latency_mapping_follows_the_throughput_mapping(handles, oracle, S, N, K, B):
+    """MINCOB_MAP_LATENCY (the lane groups of a warp share one trajectory and split the penalty samples) runs the same
+    state machine on the same numbers up to the summation order of the samples: after a few iterations both mappings
+    report the same status / iteration / evaluation counts and the same iterate (1e-7, as the oracle trace test), and
+    full runs end at points where the reported cost is the oracle's cost to 1e-9."""
+    pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=(K == 50))
+    mb = handles[S]
+    mb.set_problems(pb)
+    base = energy_only(default_params(S)) if K == 0 else default_params(S)
+    out = {}
+    for it in (3, 0):
+        for mp in (P.MAP_THROUGHPUT, P.MAP_LATENCY):
+            prm = P.MincobParams.from_buffer_copy(base)
+            prm.mapping = mp
+            prm.max_iterations = it if it else 1000
+            mb.set_params(prm)
+            out[it, mp] = mb.optimize(pb.x0())
+            assert mb.last_mapping() == (mp if N <= 16 else P.MAP_THROUGHPUT)
+    a, b = out[3, P.MAP_THROUGHPUT], out[3, P.MAP_LATENCY]
+    same = (a["evals"] == b["evals"]) & (a["iters"] == b["iters"]) & (a["status"] == b["status"])
+    assert same.mean() >= 0.97, same.mean()
+    assert rel_rows(a["x"][same], b["x"][same]) <= 1e-7
+    assert float(np.max(np.abs(a["f"][same] - b["f"][same]) / np.abs(b["f"][same]))) <= 1e-7
+    full = out[0, P.MAP_LATENCY]
+    assert ((full["status"] >= 0) | (full["status"] == P.LBFGSERR_MAXIMUMITERATION)).all()
+    fo, _ = oracle.cost_batch(base, pb, full["x"], nthreads=8)
+    assert float(np.max(np.abs(full["f"] - fo) / np.abs(fo))) <= TOL
+    # coefficients written by replica 0 are the trajectory at the final x
+    T = synth.forward_t(full["x"][:, :N])
+    np.testing.assert_allclose(full["T"], T, rtol=1e-14)
+    rel = np.abs(full["f"] - out[0, P.MAP_THROUGHPUT]["f"]) / np.abs(full["f"])
+    assert np.median(rel) <= 5e-3
+    mb.set_params(default_params(S))
+
+
+def test_latency_mapping_is_reproducible_and_batch_independent(handles):
+    """For a pinned mapping the result of a problem does not depend on what else is in the batch or on timing:
+    problem p optimized alone, in a batch of 7 and in a batch of 300 gives the same bits."""
+    prm = default_params(3, mapping=P.MAP_LATENCY)
+    mb = handles[3]
+    mb.set_params(prm)
+    pb = synth.make_problems(300, N=8, K=16, S=3)
+    mb.set_problems(pb)
+    big = mb.optimize(pb.x0())
+    for lo, hi in ((0, 1), (17, 24), (299, 300)):
+        sub = pb.slice(lo, hi)
+        mb.set_problems(sub)
+        r = mb.optimize(sub.x0())
+        for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+            np.testing.assert_array_equal(r[k], big[k][lo:hi])
+    prm.mapping = P.MAP_THROUGHPUT
+    mb.set_params(prm)
+    mb.set_problems(pb)
+    big = mb.optimize(pb.x0())
+    sub = pb.slice(40, 45)
+    mb.set_problems(sub)
+    r = mb.optimize(sub.x0())
+    for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+        np.testing.assert_array_equal(r[k], big[k][40:45])
+    mb.set_params(default_params(3))
+
+
+def test_auto_mapping(handles):
+    """MINCOB_MAP_AUTO: a single problem (the planner's call, learning_planning.cpp:143-188) and small batches take the
+    latency mapping, a batch that fills the device the throughput mapping."""
+    mb = handles[3]
+    mb.set_params(default_params(3))
+    for B, want in ((1, P.MAP_LATENCY), (64, P.MAP_LATENCY), (16384, P.MAP_THROUGHPUT)):
+        pb = synth.make_problems(B, N=5, K=16, S=3)
+        mb.set_problems(pb)
+        r = mb.optimize(pb.x0())
+        assert mb.last_mapping() == want
+        assert (r["status"] >= 0).mean() >= 0.97
+
+
+@pytest.mark.parametrize("S,N,K", [(3, 5, 16), (3, 8, 16), (4, 8, 16), (3, 12, 9)])
+def test_fixed_time_mode(handles, oracle, S, N, K):
+    """MINCOB_FLAG_FREEZE_TIMES = the call the reference makes today (qp_solver.solve with the network's times fixed,
+    learning_planner.hpp:196): the tau block of the gradient is zero, the durations come back bit-identical, only the
+    waypoints move; cost/gradient parity with the oracle in the same mode 1e-9, converged costs as in the free mode."""
+    prm = default_params(S, flags=P.FLAG_FREEZE_TIMES)
+    pb = synth.make_problems(128, N=N, K=K, S=S, ragged_rows=(K == 9))
+    mb = handles[S]
+    mb.set_params(prm)
+    mb.set_problems(pb)
+    x0 = pb.x0()
+    f, g = mb.evaluate(x0)
+    fo, go = oracle.cost_batch(prm, pb, x0, nthreads=8)
+    assert (g[:, :N] == 0.0).all() and (go[:, :N] == 0.0).all()
+    assert float(np.max(np.abs(f - fo) / np.abs(fo))) <= TOL and rel_rows(g, go) <= TOL
+    for mp in (P.MAP_THROUGHPUT, P.MAP_LATENCY):
+        prm.mapping = mp
+        mb.set_params(prm)
+        res = mb.optimize(x0)
+        np.testing.assert_array_equal(res["x"][:, :N], x0[:, :N])           # durations untouched
+        np.testing.assert_allclose(res["T"], pb.T0, rtol=1e-14)
+        assert (res["status"] >= 0).mean() >= 0.97
+        assert (res["f"] < f).all()
+        fo2, _ = oracle.cost_batch(prm, pb, res["x"], nthreads=8)
+        assert float(np.max(np.abs(res["f"] - fo2) / np.abs(fo2))) <= TOL
+    ref = oracle.optimize_batch(prm, pb, nthreads=8)
+    np.testing.assert_array_equal(ref["x"][:, :N], x0[:, :N])
+    rel = np.abs(res["f"] - ref["f"]) / np.abs(ref["f"])
+    assert np.median(rel) <= 2e-3, np.median(rel)
+    mb.set_params(default_params(S))
+
+
+def test_planner_rows_flag(handles, oracle):
+    """MINCOB_FLAG_PLANNER_ROWS: rows [n, b] with n.p <= b (what LearningPlanner::plan produces, learning_planner.hpp:
+    293-299) give bit-identical results to the same rows in GCOPTER sign [n, -b]; host and device entry points."""
+    import torch
+    pb = synth.make_problems(200, N=5, K=50, S=3, ragged_rows=True)
+    pl = pb.slice(0, pb.B)
+    pl.hpolys = pb.hpolys.copy()      # slice() shares memory with pb when the range is the whole batch
+    pl.hpolys[..., 3] *= -1.0
+    mb = handles[3]
+    mb.set_params(default_params(3))
+    mb.set_problems(pb)
+    f0, g0 = mb.evaluate(pb.x0())
+    prm = default_params(3, flags=P.FLAG_PLANNER_ROWS)
+    mb.set_params(prm)
+    mb.set_problems(pl)
+    f1, g1 = mb.evaluate(pb.x0())
+    np.testing.assert_array_equal(f0, f1); np.testing.assert_array_equal(g0, g1)
+    fo, go = oracle.cost_batch(prm, pl, pb.x0(), nthreads=8)
+    assert float(np.max(np.abs(f1 - fo) / np.abs(fo))) <= TOL and rel_rows(g1, go) <= TOL
+    dev = torch.device("cuda:0")
+    th = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    head, tail, hp, hr, x = th(pl.head), th(pl.tail), th(pl.hpolys), th(pl.hrows), th(pb.x0())
+    hp_before = hp.clone()
+    mb.set_problems_device(pl.B, pl.N, pl.K, head, tail, hp, hr)
+    f2 = torch.empty(pl.B, dtype=torch.float64, device=dev); g2 = torch.empty_like(x)
+    mb.evaluate_device(x, f2, g2)
+    mb.synchronize()
+    np.testing.assert_array_equal(f2.cpu().numpy(), f0); np.testing.assert_array_equal(g2.cpu().numpy(), g0)
+    assert torch.equal(hp, hp_before)                    # the caller's rows are not modified
+    mb.set_params(default_params(3))
+
+
+@pytest.mark.parametrize("mem,past", [(1, 0), (3, 3), (16, 8), (8, 0)])
+def test_rolled_two_loop_recursion_on_device(handles, oracle, mem, past):
+    """mem_size != 8 takes the rolled two-loop recursion (ring indexing through shared alpha / y.s arrays), `past`
+    0 / 8 the extremes of the past-cost ring: same control flow as the oracle for a few iterations, and full runs
+    converge like it."""
+    pb = synth.make_problems(192, N=8, K=16, S=3)
+    mb = handles[3]
+    mb.set_problems(pb)
+    for iters in (2, 5):
+        prm = default_params(3, mem_size=mem, past=past, max_iterations=iters)
+        mb.set_params(prm)
+        res = mb.optimize(pb.x0())
+        ref = oracle.optimize_batch(prm, pb, nthreads=8)
+        same = (res["evals"] == ref["evals"]) & (res["iters"] == ref["iters"]) & (res["status"] == ref["status"])
+        assert same.mean() >= 0.98, (mem, past, iters, same.mean())
+        assert rel_rows(res["x"][same], ref["x"][same]) <= 1e-7
+    prm = default_params(3, mem_size=mem, past=past, max_iterations=400 if past == 0 else 1000)
+    mb.set_params(prm)
+    res = mb.optimize(pb.x0())
+    ref = oracle.optimize_batch(prm, pb, nthreads=8)
+    fo, _ = oracle.cost_batch(prm, pb, res["x"], nthreads=8)
+    assert float(np.max(np.abs(res["f"] - fo) / np.abs(fo))) <= TOL
+    rel = np.abs(res["f"] - ref["f"]) / np.abs(ref["f"])
+    assert np.median(rel) <= 5e-3, np.median(rel)
+    mb.set_params(default_params(3))
+
+
+def test_autograd_layer_on_the_default_stream_large_batch(handles):
+    """on torch's default stream (handle 0) the layer must be ordered with the torch kernels that
+    produce its inputs and consume its outputs.  A large batch whose inputs are produced by a chain of torch
+    kernels right before the call, compared with the same call after a full synchronisation."""
+    import torch
+    from allocnet_b200.autograd import minco_layer
+    dev = torch.device("cuda:0")
+    S, N, B = 3, 8, 60000
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    mb = handles[S]
+    head = torch.randn(B, S, 3, dtype=torch.float64, device=dev, generator=g)
+    tail = torch.randn(B, S, 3, dtype=torch.float64, device=dev, generator=g)
+    base_q = torch.randn(B, N - 1, 3, dtype=torch.float64, device=dev, generator=g)
+    base_T = torch.rand(B, N, dtype=torch.float64, device=dev, generator=g) + 0.5
+    torch.cuda.synchronize()
+    assert torch.cuda.current_stream(dev).cuda_stream == 0
+
+    def run(sync_first):
+        q = base_q.clone().requires_grad_(True); T = base_T.clone().requires_grad_(True)
+        qq, TT = q, T
+        for _ in range(30):                      # a queue of default-stream kernels the layer has to wait for
+            qq = qq * 1.0000001 + 1e-9; TT = TT * 1.0000001 + 1e-9
+        if sync_first:
+            torch.cuda.synchronize()
+        e, c = minco_layer(mb, head, tail, qq, TT)
+        loss = (e * 1e-3).sum() + (c * c).sum() * 1e-3
+        loss.backward()
+        if sync_first:
+            torch.cuda.synchronize()
+        return loss.detach().clone(), q.grad.clone(), T.grad.clone()
+    la, gqa, gTa = run(True)
+    for _ in range(3):
+        lb, gqb, gTb = run(False)
+        assert torch.equal(la, lb) and torch.equal(gqa, gqb) and torch.equal(gTa, gTb)
+    mb.set_stream(None)

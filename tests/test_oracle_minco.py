@@ -537,3 +537,25 @@ def test_reference_max_rates_septic_against_dense_sampling(oracle):
             assert abs(ref.ref_traj7_max_acc_rate(h) - want[1]) <= 1e-7 * want[1]
         finally:
             ref.ref_traj7_destroy(h)
+
+
+def test_oracle_fixed_time_and_planner_row_flags(oracle):
+    """mincob_params.flags in the oracle: FREEZE_TIMES zeroes the tau block of the gradient and leaves f and the
+    waypoint block unchanged; PLANNER_ROWS on rows [n, b] (n.p <= b, learning_planner.hpp:293-299) equals the
+    GCOPTER-sign rows [n, -b] bit for bit; lbfgs_optimize in fixed-time mode never moves tau."""
+    from allocnet_b200 import params as P
+    pb = synth.make_problems(24, N=5, K=16, S=3)
+    x = pb.x0()
+    f0, g0 = oracle.cost_batch(default_params(3), pb, x)
+    f1, g1 = oracle.cost_batch(default_params(3, flags=P.FLAG_FREEZE_TIMES), pb, x)
+    np.testing.assert_array_equal(f0, f1)
+    assert (g1[:, :5] == 0).all() and (np.abs(g0[:, :5]).max(axis=1) > 0).all()
+    np.testing.assert_array_equal(g0[:, 5:], g1[:, 5:])
+    pl = pb.slice(0, pb.B); pl.hpolys = pb.hpolys.copy(); pl.hpolys[..., 3] *= -1.0
+    f2, g2 = oracle.cost_batch(default_params(3, flags=P.FLAG_PLANNER_ROWS), pl, x)
+    np.testing.assert_array_equal(f0, f2); np.testing.assert_array_equal(g0, g2)
+    r = oracle.optimize_batch(default_params(3, flags=P.FLAG_FREEZE_TIMES), pb)
+    np.testing.assert_array_equal(r["x"][:, :5], x[:, :5])
+    assert (r["status"] >= 0).all() and (r["f"] < f0).all()
+    rf = oracle.optimize_batch(default_params(3), pb)
+    assert (rf["f"] <= r["f"] * (1 + 1e-6)).mean() >= 0.9      # freeing the durations can only help

@@ -92,3 +92,57 @@ def test_pack_inputs_layout_and_warm_start_shapes():
     assert float(hp[:, 16:].abs().max()) == 0.0
     T0 = timealloc.warm_start_durations(timealloc.random_weights(seed=5), pb)
     assert T0.shape == (6, 8) and (T0 > 0).all()
+
+
+# ---- the reference's trained weights, exported to tests/golden/timealloc_seq5.npz (make_timealloc_fixture.py) -------
+
+def test_fixture_weights_reproduce_reference_outputs_cpu():
+    """forward_batched with the exported state_dict == what the reference's TorchScript model answered, sample by
+    sample, when the fixture was made (random planner-shaped inputs and inputs packed from the corridor generator)."""
+    z = np.load(timealloc.FIXTURE)
+    w = timealloc.load_weights_npz()
+    assert sum(v.numel() for v in w.values()) == 311656                   # SURVEY.md Appendix D.2
+    got = timealloc.forward_batched(w, torch.from_numpy(z["rand_state"]), torch.from_numpy(z["rand_hpolys"])).numpy()
+    np.testing.assert_allclose(got, z["rand_times"], rtol=0, atol=5e-6)
+    assert (z["rand_times"] == 0).any() and (z["rand_times"][:, 1] != 0).any()
+    pb = synth.make_problems(96, N=5, K=16, S=3)
+    st, hp = timealloc.pack_inputs(pb.head, pb.tail, pb.hpolys, pb.hrows, 0, 5)
+    got = timealloc.forward_batched(w, st, hp).numpy()
+    np.testing.assert_allclose(got, z["synth_times"], rtol=0, atol=5e-6)
+    # the torch packing used on the device equals the numpy one
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    st2, hp2 = timealloc.pack_inputs_torch(t(pb.head), t(pb.tail), t(pb.hpolys), t(pb.hrows), 0, 5)
+    np.testing.assert_array_equal(st2.numpy(), st.numpy()); np.testing.assert_array_equal(hp2.numpy(), hp.numpy())
+    if os.path.exists(REF_MODEL):                                          # the fixture is the model's state_dict
+        w2 = timealloc.load_weights(REF_MODEL)
+        for k in w2:
+            assert torch.equal(w[k], w2[k])
+
+
+def test_windowed_warm_start_torch_equals_numpy():
+    w = timealloc.load_weights_npz()
+    pb = synth.make_problems(40, N=16, K=16, S=3)
+    want = timealloc.warm_start_durations(w, pb)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    got, acc = timealloc.warm_start_durations_torch(w, t(pb.head), t(pb.tail), t(pb.hpolys), t(pb.hrows), t(pb.q0), t(pb.T0), chunk=16)
+    np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=1e-6)      # fp32 net, batch chunking changes the GEMM blocking
+    assert acc.shape == (40, 4)
+
+
+@pytest.mark.gpu
+def test_fixture_weights_reproduce_reference_outputs_cuda():
+    """Same golden vectors, net on cuda:0 (cuDNN/cuBLAS fp32: 2e-5)."""
+    z = np.load(timealloc.FIXTURE)
+    dev = torch.device("cuda:0")
+    w = timealloc.load_weights_npz(device=dev)
+    got = timealloc.forward_batched(w, torch.from_numpy(z["rand_state"]).to(dev), torch.from_numpy(z["rand_hpolys"]).to(dev))
+    np.testing.assert_allclose(got.cpu().numpy(), z["rand_times"], rtol=0, atol=2e-5)
+    pb = synth.make_problems(96, N=5, K=16, S=3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    st, hp = timealloc.pack_inputs_torch(t(pb.head), t(pb.tail), t(pb.hpolys), t(pb.hrows), 0, 5)
+    got = timealloc.forward_batched(w, st, hp)
+    # the stop decision (sigmoid > 0.5) may flip for a sample whose token sits at the threshold: compare where both agree
+    gn, zn = got.cpu().numpy(), z["synth_times"]
+    same = ((gn != 0) == (zn != 0)).all(axis=1)
+    assert same.mean() >= 0.97
+    np.testing.assert_allclose(gn[same], zn[same], rtol=0, atol=2e-5)
