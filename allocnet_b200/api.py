@@ -34,7 +34,8 @@ SYMBOLS = [
     "mincob_comm_destroy", "mincob_optimize_sharded", "mincob_host_alloc", "mincob_host_free",
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
     "mincob_max_rates", "mincob_max_rates_device", "mincob_minco_forward_device", "mincob_minco_propagate_device",
-    "mincob_optimize_sharded_local", "mincob_gathered_device", "mincob_last_mapping",
+    "mincob_optimize_sharded_local", "mincob_gathered_device", "mincob_last_mapping", "mincob_host_register",
+    "mincob_host_unregister",
 ]
 
 
@@ -81,6 +82,9 @@ def load_library() -> C.CDLL:
     L.mincob_gathered_device.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]
     L.mincob_host_alloc.argtypes = [C.POINTER(_vp), C.c_uint64]
     L.mincob_host_free.argtypes = [_vp]
+    if hasattr(L, "mincob_host_register"):
+        L.mincob_host_register.argtypes = [_vp, C.c_uint64]
+        L.mincob_host_unregister.argtypes = [_vp]
     L.mincob_check_feasibility.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_check_feasibility_device.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     L.mincob_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
@@ -343,6 +347,18 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
     weakref.finalize(buf, L.mincob_host_free, _vp(p.value))
     return arr
+
+
+def host_register(arr: np.ndarray) -> None:
+    """Page-lock an existing numpy buffer (mincob_host_register), e.g. one over multiprocessing.shared_memory."""
+    L = load_library()
+    rc = L.mincob_host_register(_vp(arr.ctypes.data), arr.nbytes)
+    if rc != 0:
+        raise MincobError(f"mincob_host_register({arr.nbytes}): {L.mincob_strerror(rc).decode()}")
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    load_library().mincob_host_unregister(_vp(arr.ctypes.data))
 
 
 def lbfgs_strerror(status: int) -> str:

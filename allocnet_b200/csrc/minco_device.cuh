@@ -606,6 +606,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
         }
         const int jend = min(JB, cnt - j0);
         constexpr int UJ = MINCOB_UNROLL_JJ;
+
 #pragma unroll UJ
         for (int jj = 0; jj < jend; ++jj) {
             const int j = sample(j0 + jj);

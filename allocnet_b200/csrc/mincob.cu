@@ -841,6 +841,16 @@ int mincob_host_alloc(void **out, uint64_t bytes) {
     *out = nullptr;
     return cudaHostAlloc(out, bytes ? (size_t)bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : MINCOB_E_ALLOC;
 }
+// page-lock memory the caller already owns (e.g. a POSIX shared-memory segment mapped by every rank of a node, so
+// that each rank's device-to-host copy lands directly in the consumer's address space)
+int mincob_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return MINCOB_E_INVALID;
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? 0 : MINCOB_E_CUDA;
+}
+int mincob_host_unregister(void *p) {
+    if (!p) return 0;
+    return cudaHostUnregister(p) == cudaSuccess ? 0 : MINCOB_E_CUDA;
+}
 int mincob_host_free(void *p) {
     if (!p) return 0;
     return cudaFreeHost(p) == cudaSuccess ? 0 : MINCOB_E_CUDA;

@@ -49,10 +49,34 @@ def bytes_traj_once(N: int, S: int = 3) -> int:
     return N * 3 * 2 * S * 8
 
 
+CONFIGS = {  # BASELINE.json configs[1..4] (configs[0] is the CPU-only single solve)
+    2: dict(batch=4096, pieces=8, K=0),                       # energy-only
+    3: dict(batch=65536, pieces=8, K=16),                     # headline: the configuration the metric is quoted on
+    4: dict(batch=65536, pieces=16, K=16, warm_start="net"),  # learned time-allocation warm start (seq5 conv-lstm)
+    5: dict(batch=65536, pieces=8, K=16),                     # per GPU; 8 ranks = 524 288 problems + all-gather
+}
+
+
 def workload_name(a) -> str:
     pen = "corridor K=%d + vel/acc/jerk penalties" % a.K if a.K > 0 else "energy-only"
-    return (f"configs[2]: batch {a.batch} x {a.pieces}-piece per GPU, {pen}, S={a.S} "
-            f"({'MINCO_S3NU jerk' if a.S == 3 else 'MINCO_S4NU snap'}), fp64, L-BFGS mem_size={a.mem_size}")
+    ws = ("; initial durations from the reference's seq5 conv-lstm net on sliding 5-piece windows (trapezoid rule where "
+          "the planner would reject the net's answer)") if a.warm_start == "net" else ""
+    fz = "; durations FIXED (MINCOB_FLAG_FREEZE_TIMES)" if a.freeze_times else ""
+    return (f"configs[{a.config}]: batch {a.batch} x {a.pieces}-piece per GPU, {pen}, S={a.S} "
+            f"({'MINCO_S3NU jerk' if a.S == 3 else 'MINCO_S4NU snap'}), fp64, L-BFGS mem_size={a.mem_size}{ws}{fz}")
+
+
+def host_info() -> dict:
+    model = "?"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"cpu_model": model, "logical_cpus": os.cpu_count()}
 
 
 class ClockSampler:
@@ -110,7 +134,11 @@ class ClockSampler:
 
 def make_params(a):
     from allocnet_b200.params import default_params, energy_only
+    from allocnet_b200 import params as P
     p = default_params(a.S, mem_size=a.mem_size)
+    p.mapping = {"auto": P.MAP_AUTO, "throughput": P.MAP_THROUGHPUT, "latency": P.MAP_LATENCY}[getattr(a, "mapping", "auto")]
+    if getattr(a, "freeze_times", False):
+        p.flags |= P.FLAG_FREEZE_TIMES
     return p if a.K > 0 else energy_only(p)
 
 
@@ -147,14 +175,30 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample_per_step": sample},
+        "config": {"workload": workload_name(a) + f"; CPU arm: each step is a bounded sample of {sample} problems of that "
+                               "workload's seeded stream (trajectories/s does not depend on the batch size on the CPU: "
+                               "problems are independent and run one per thread)",
+                   "sample_per_step": sample, "host": host_info()},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": thr, "kind": kind,
-                         "sample": f"{sample} problems per step x {a.steps} steps of the same seeded stream; driver: {drv}",
-                         "evals_per_s": evals / tot, "mean_evals_per_traj": evals / trajs},
+                         "sample": f"{sample} problems per step x {a.steps} steps of the same seeded stream; driver: {drv}; "
+                                   "cost functional: oracle/minco_oracle.hpp (restated MINCO, -O3 -march=x86-64-v3)",
+                         "evals_per_s": evals / tot, "mean_evals_per_traj": evals / trajs, "host": host_info()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def sass_fingerprint():
+    """Identity of the built optimize kernel: size and mtime-independent hash of allocnet_b200/libmincob.so; the fp64 flop
+    count per evaluation in profiles/optimize_kernel_traffic.json is only valid for the build it was captured from."""
+    import hashlib
+    from allocnet_b200 import api
+    try:
+        with open(api.LIB_PATH, "rb") as fh:
+            return hashlib.sha256(fh.read()).hexdigest()[:16]
+    except OSError:
+        return None
 
 
 def main():
@@ -163,15 +207,27 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU per step")
-    ap.add_argument("--pieces", type=int, default=8)
-    ap.add_argument("--K", type=int, default=16)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[] preset (3 = headline); --batch/--pieces/--K override it")
+    ap.add_argument("--batch", type=int, default=None, help="problems per GPU per step")
+    ap.add_argument("--pieces", type=int, default=None)
+    ap.add_argument("--K", type=int, default=None)
     ap.add_argument("--S", type=int, default=3)
     ap.add_argument("--mem-size", dest="mem_size", type=int, default=8)
+    ap.add_argument("--warm-start", dest="warm_start", default=None, choices=["trapezoid", "net"])
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=0)
+    ap.add_argument("--mapping", default="auto", choices=["auto", "throughput", "latency"],
+                    help="mincob_params.mapping: lanes-per-trajectory layout of the optimize kernel")
+    ap.add_argument("--freeze-times", action="store_true", help="MINCOB_FLAG_FREEZE_TIMES: durations fixed (the reference's call)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity / gather checks (they run outside the timed region)")
     a = ap.parse_args()
+    preset = CONFIGS[a.config]
+    a.batch = a.batch if a.batch is not None else preset["batch"]
+    a.pieces = a.pieces if a.pieces is not None else preset["pieces"]
+    a.K = a.K if a.K is not None else preset["K"]
+    a.warm_start = a.warm_start or preset.get("warm_start", "trapezoid")
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
     if a.impl == "reference":
@@ -181,6 +237,7 @@ def main():
     import torch
     import torch.distributed as dist
     from allocnet_b200 import api, sharded, synth
+    from allocnet_b200 import params as PR
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,7 +264,7 @@ def main():
     mb = sh.mb
 
     # ---- device-resident leg -------------------------------------------------------------
-    t = lambda arr: torch.from_numpy(arr).to(dev)
+    t = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
     d_head, d_tail = t(pb.head), t(pb.tail)
     d_hp = t(pb.hpolys) if K > 0 else None
     d_hr = t(pb.hrows) if K > 0 else None
@@ -220,14 +277,47 @@ def main():
     d_T = torch.empty(B, N, dtype=torch.float64, device=dev)
     cnt = B * N * 3 * 2 * S
     d_all = torch.empty(world * cnt, dtype=torch.float64, device=dev)   # gathered coefficients, rank-major
-    d_coeffs = d_all[rank * cnt:(rank + 1) * cnt] if world == 1 else torch.empty(cnt, dtype=torch.float64, device=dev)
+    d_coeffs = d_all[rank * cnt:(rank + 1) * cnt]    # the kernel writes this rank's block in place: in-place ncclAllGather
     mb.set_problems_device(B, N, K, d_head, d_tail, d_hp, d_hr)
 
-    kernel_ms = []
+    # config 4: the reference's trained time-allocation net gives the initial durations; it runs
+    # INSIDE the step, batched on the device, on sliding 5-piece windows
+    net = None
+    if a.warm_start == "net":
+        if K == 0:
+            raise SystemExit("--warm-start net needs corridor rows (K > 0)")
+        from allocnet_b200 import timealloc
+        net = {"w": timealloc.load_weights_npz(device=dev), "q0": t(pb.q0), "T0": t(pb.T0), "ta": timealloc,
+               "accepted": None, "ms": []}
+
+    def net_x0():
+        T, acc = net["ta"].warm_start_durations_torch(net["w"], d_head, d_tail, d_hp, d_hr, net["q0"], net["T0"])
+        net["accepted"] = acc
+        big = torch.sqrt(torch.clamp(2.0 * T - 1.0, min=0.0)) - 1.0           # backwardT
+        small = 1.0 - torch.sqrt(torch.clamp(2.0 / T - 1.0, min=0.0))
+        d_x[:, :N] = torch.where(T > 1.0, big, small)
+        d_x[:, N:] = d_x0[:, N:]
+
+    kernel_ms, gather_ev = [], []
 
     def step(record: bool):
-        d_x.copy_(d_x0)                                   # fresh start point (x is in/out)
-        sh.optimize_and_gather_device(d_x, d_f, d_status, d_iters, d_evals, d_coeffs, d_T, d_all, cnt)
+        if net is not None:
+            e_n0, e_n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_n0.record(stream)
+            net_x0()
+            e_n1.record(stream)
+            if record:
+                net["ms"].append((e_n0, e_n1))
+        else:
+            d_x.copy_(d_x0)                               # fresh start point (x is in/out)
+        mb.optimize_device(d_x, d_f, d_status, d_iters, d_evals, d_coeffs, d_T)
+        if world > 1:
+            e_g0, e_g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_g0.record(stream)
+            mb.allgather_device(d_coeffs, d_all, cnt)     # sendbuf == recvbuf + rank*count: in place
+            e_g1.record(stream)
+            if record:
+                gather_ev.append((e_g0, e_g1))
         if record:
             kernel_ms.append(mb.last_kernel_ms()[0])      # CUDA events around the launch, on its stream
 
@@ -255,6 +345,20 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_tot = float(tms.item())
+    mapping = {PR.MAP_THROUGHPUT: "throughput (one lane per piece)", PR.MAP_LATENCY: "latency (one warp per trajectory)"}.get(
+        mb.last_mapping() if hasattr(mb.L, "mincob_last_mapping") else 0, "?")
+    # attribution of the step on every rank: optimize kernel, all-gather (device events), max / min over ranks
+    k_ms_rank = float(np.mean(kernel_ms))
+    g_ms_rank = float(np.mean([x.elapsed_time(y) for x, y in gather_ev])) if gather_ev else 0.0
+    per_rank = torch.tensor([k_ms_rank, g_ms_rank], dtype=torch.float64, device=dev)
+    ranks_ms = [per_rank.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ranks_ms, per_rank)
+    ranks_ms = torch.stack(ranks_ms).cpu().numpy()
+    evals_t = d_evals.to(torch.int64).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(evals_t)
+    evals_all = int(evals_t.item())
     evals_sum = int(d_evals.to(torch.int64).sum().item())
     iters_mean = float(d_iters.to(torch.float64).mean().item())
     status = d_status.cpu().numpy()
@@ -263,13 +367,52 @@ def main():
     status_hist = {str(int(c)): int(k) for c, k in zip(codes, cnts)}
     evals_np = d_evals.cpu().numpy()
 
+    # ---- checks, outside the timed region -------------------------------------------------------------------
+    parity = None
+    if not a.no_check:
+        parity = {}
+        # (1) the device's cost at its final x against the CPU oracle at the same x, first `nchk` problems of this rank
+        from oracle.pyoracle import Oracle
+        nchk = min(B, 4096)
+        orc = Oracle()
+        xf = d_x[:nchk].cpu().numpy()
+        fo, _ = orc.cost_batch(prm, pb.slice(0, nchk), xf, nthreads=orc.hardware_threads() or 1)
+        fd = d_f[:nchk].cpu().numpy()
+        okp = status[:nchk] != PR.LBFGSERR_INVALID_FUNCVAL
+        rel = np.abs(fd - fo)[okp] / np.abs(fo)[okp]
+        mr = torch.tensor([float(rel.max()) if rel.size else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mr, op=dist.ReduceOp.MAX)
+        parity.update({"max_rel": float(mr.item()), "n": int(nchk) * world, "tolerance": 1e-9,
+                       "what": "device cost at the device's final x vs oracle cost_batch at that x (every rank, max)"})
+        # (2) gathered array: every rank checks that each rank's block of ITS gathered copy carries that rank's own
+        #     checksum (a checksum of checksums), and that its own block is bit-identical to what its kernel wrote
+        if world > 1:
+            blocks = d_all.view(torch.int64).reshape(world, cnt)
+            sums = blocks.sum(dim=1)                                   # wrapping int64 sums of the bit patterns
+            mine = sums[rank].clone().reshape(1)
+            want = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(want, mine)
+            good = torch.tensor([int(all(int(w.item()) == int(sums[r].item()) for r, w in enumerate(want)))],
+                                dtype=torch.int64, device=dev)
+            # coefficients of problem p evaluated at t = 0 must be the waypoint the optimizer returned for it
+            pos0 = blocks.view(torch.float64).reshape(world, B, N, 3, 2 * S)[rank, :, 1:, :, 2 * S - 1]
+            good &= int(torch.equal(pos0, d_x[:, N:].reshape(B, N - 1, 3))) if N > 1 else 1
+            dist.all_reduce(good, op=dist.ReduceOp.MIN)
+            parity["gather_ok"] = bool(int(good.item()))
+            parity["gather_check"] = "int64 checksum of every rank's block in every rank's gathered copy == that rank's own; start positions of the gathered pieces == returned waypoints"
+        else:
+            parity["gather_ok"] = True
+            parity["gather_check"] = "single rank: no collective"
+
     # ---- quality of what was produced (outside the timed region): sampled limits and corridor residual ----
     d_rep = torch.empty(B, 4, dtype=torch.float64, device=dev)
-    mb.check_feasibility_device(d_coeffs, d_T, 32, d_rep)
+    d_co = d_coeffs.contiguous()
+    mb.check_feasibility_device(d_co, d_T, 32, d_rep)
     torch.cuda.synchronize(dev)
     rep = d_rep.cpu().numpy()
     d_rates = torch.empty(B, 3, dtype=torch.float64, device=dev)
-    mb.max_rates_device(d_coeffs, d_T, d_rates)                        # exact maxima (Trajectory::getMaxVelRate ...)
+    mb.max_rates_device(d_co, d_T, d_rates)                            # exact maxima (Trajectory::getMaxVelRate ...)
     torch.cuda.synchronize(dev)
     rates = d_rates.cpu().numpy()
     quality = {"samples_per_piece": 33,
@@ -281,6 +424,24 @@ def main():
                "j_within_2pct": float((rep[:, 2] <= 1.02 * float(prm.j_max)).mean()),
                "corridor_within_2cm": float((rep[:, 3] <= 0.02).mean()) if K > 0 else None,
                "max_speed_p99": float(np.percentile(rep[:, 0], 99))}
+
+    # ---- config 4: the same batch from the trapezoid start, for comparison (untimed in `value`) ----------------
+    warm = None
+    if net is not None:
+        acc = net["accepted"]
+        net_ms = float(np.mean([x.elapsed_time(y) for x, y in net["ms"]]))
+        d_x.copy_(d_x0)
+        mb.optimize_device(d_x, d_f, d_status, d_iters, d_evals, d_coeffs, d_T)
+        trap_ms = mb.last_kernel_ms()[0]
+        warm = {"model": "seq5_tokenthresh0_35 (state_dict exported to tests/golden/timealloc_seq5.npz)",
+                "windows_per_trajectory": int(acc.shape[1]), "accepted_window_fraction": float(acc.double().mean().item()),
+                "accepted_trajectory_fraction": float(acc.all(dim=1).double().mean().item()),
+                "net_forward_ms_per_step": net_ms, "optimize_ms_net_start": k_ms_rank,
+                "mean_evals_net_start": evals_sum / B,
+                "optimize_ms_trapezoid_start": float(trap_ms),
+                "mean_evals_trapezoid_start": float(d_evals.to(torch.float64).mean().item()),
+                "note": "windows whose net answer the planner would reject (a duration < 1e-10 on a used segment, i.e. the stop "
+                        "token fired early: learning_planner.hpp:181-189) keep the trapezoid rule"}
 
     # ---- the per-evaluation kernel on its own (the lbfgs_evaluate_t body for the whole batch, one launch): this is the
     #      launch BASELINE.json's "one fused kernel per L-BFGS evaluation" describes, with its algorithmic HBM bytes -------
@@ -309,9 +470,25 @@ def main():
         h_x0, h_x = pin((B, n)), pin((B, n))
         h_f, h_T = pin((B,)), pin((B, N))
         h_status, h_iters, h_evals = pin((B,), np.int32), pin((B,), np.int32), pin((B,), np.int32)
-        # rank 0 is the consumer of the whole job: it reads back the coefficients of every rank (rank-major); the other
-        # ranks take part in the same all-gather and read back their own shard only
-        h_call = pin((world * cnt,)) if rank == 0 else pin((cnt,))
+        # Where the job's result lands: ONE host array [world*B][N][3][2S] (rank-major) in the consumer's (rank 0's) memory.
+        # With several ranks it is a shared-memory segment mapped and page-locked by every rank, and every rank copies its own
+        # block device -> host into it over its own PCIe link (mincob_optimize_sharded_local); the device-side all-gather of
+        # the step is the same collective as in the device-resident leg.
+        shm = None
+        if world > 1:
+            from multiprocessing import shared_memory
+            box = [None]
+            if rank == 0:
+                shm = shared_memory.SharedMemory(create=True, size=world * cnt * 8)
+                box[0] = shm.name
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=box[0])
+            h_call_all = np.ndarray((world * cnt,), dtype=np.float64, buffer=shm.buf)
+            api.host_register(h_call_all)
+            h_call = h_call_all[rank * cnt:(rank + 1) * cnt]
+        else:
+            h_call_all = h_call = pin((cnt,))
         h_head[...] = pb.head; h_tail[...] = pb.tail; h_x0[...] = pb.x0()
         if K > 0:
             h_hp[...] = pb.hpolys; h_hr[...] = pb.hrows
@@ -324,32 +501,43 @@ def main():
         def e2e_step():
             h_x[...] = h_x0
             mb.set_problems(hpb)                                       # H2D: head, tail, hpolys, hrows
-            if rank == 0:
-                mb.optimize_sharded_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)   # H2D x; D2H results
-            else:
-                mb.optimize_sharded_local_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)
+            # H2D x; optimize; all-gather on the device; D2H of this rank's results into the shared result array
+            mb.optimize_sharded_local_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)
         for _ in range(2):
             e2e_step()
         fence()
         t0 = time.perf_counter()
         for _ in range(a.steps):
             e2e_step()                                                 # returns after the results are on the host
-        fence()
+        fence()                                                        # every rank's block is in the consumer's array
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ok = True
+        if not a.no_check and rank == 0:                               # the consumer sees every rank's block
+            got = h_call_all.reshape(world, B, N, 3, 2 * S)
+            e2e_ok = bool(np.isfinite(got).all()) and bool((np.abs(got).reshape(world, -1).max(axis=1) > 0).all())
+            e2e_ok = e2e_ok and bool(np.array_equal(got[0, :, 1:, :, 2 * S - 1], h_x[:, N:].reshape(B, N - 1, 3)) if N > 1 else True)
         h2d = pb.head.nbytes + pb.tail.nbytes + (pb.hpolys.nbytes + pb.hrows.nbytes if K > 0 else 0) + B * n * 8
-        d2h = B * n * 8 + B * 8 + 3 * B * 4 + world * cnt * 8 + B * N * 8
+        d2h = B * n * 8 + B * 8 + 3 * B * 4 + cnt * 8 + B * N * 8
         e2e = {"value": world * B * a.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / a.steps,
-               "api": "mincob_set_problems + mincob_optimize_sharded (host pointers, pinned)" +
-                      ("; rank 0 reads back all ranks' coefficients (d2h_bytes_per_step is rank 0's), the other ranks "
-                       "(mincob_optimize_sharded_local) their own shard" if world > 1 else ""),
-               "ok_fraction": float((h_status >= 0).mean())}
+               "api": "mincob_set_problems + mincob_optimize_sharded_local (host pointers, pinned)" +
+                      ("; bytes are per rank; every rank copies its own block of the result into one shared, page-locked host "
+                       "array owned by rank 0 (the consumer), after the device-side all-gather" if world > 1 else ""),
+               "ok_fraction": float((h_status >= 0).mean()), "result_complete_on_consumer": e2e_ok}
+        if shm is not None:
+            fence()
+            api.host_unregister(h_call_all)
+            del h_call, h_call_all
+            shm.close()
+            if rank == 0:
+                shm.unlink()
         mb.set_problems_device(B, N, K, d_head, d_tail, d_hp, d_hr)
 
     if rank == 0:
-        k_ms = float(np.mean(kernel_ms))
+        k_ms = float(ranks_ms[:, 0].max())                 # the slowest rank's kernel is the one the step waits for
+        k_ms0 = float(ranks_ms[0, 0])
         alg = evals_sum * bytes_eval(N, K, S) + B * bytes_traj_once(N, S)
         peaks, peak_src = None, "fallback (B200_PROFILING.md)"
         try:
@@ -358,23 +546,29 @@ def main():
             peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             peak = 6650.0
-        achieved = alg / (k_ms * 1e-3) / 1e9
+        achieved = alg / (k_ms0 * 1e-3) / 1e9
         traffic, fp64 = None, None
         try:  # dram bytes and fp64 flops of one launch from the committed `ncu --set full` capture, if any
             with open(os.path.join(ROOT, "profiles", "optimize_kernel_traffic.json")) as fh:
                 tj = json.load(fh)
             if tj.get("batch") == B and tj.get("pieces") == N and tj.get("K") == K and tj.get("S", 3) == S:
                 traffic = tj.get("dram_bytes_per_launch")
-                if tj.get("fp64_flops_per_eval"):
+                stale = tj.get("library_sha256_16") not in (None, sass_fingerprint())
+                if tj.get("fp64_flops_per_eval") and not stale:
                     # what actually bounds the kernel: executed fp64 flops (2 per DFMA, 1 per DADD/DMUL, predicated-on
                     # threads only; counted by ncu per evaluation for this configuration) over the live kernel time,
                     # against the DFMA rate measured on this device a moment ago
                     fl = float(tj["fp64_flops_per_eval"]) * evals_sum
                     pk = mb.measure_fp64_peak()
-                    fp64 = {"bound": "fp64", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
-                            "frac": fl / (k_ms * 1e-3) / 1e12 / pk, "flops_per_eval": float(tj["fp64_flops_per_eval"]),
+                    fp64 = {"bound": "fp64", "achieved": fl / (k_ms0 * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
+                            "frac": fl / (k_ms0 * 1e-3) / 1e12 / pk, "flops_per_eval": float(tj["fp64_flops_per_eval"]),
                             "peak_source": "mincob_measure_fp64_peak (independent DFMA chains, CUDA events, this run)",
                             "flops_source": tj.get("source")}
+                elif stale:
+                    traffic = None
+                    print("[bench] profiles/optimize_kernel_traffic.json was captured from another build of libmincob.so "
+                          "(library_sha256_16 differs): traffic / roofline_fp64 withheld; re-run tools/update_profiles.py",
+                          file=sys.stderr)
         except Exception as e:
             print(f"[bench] no traffic / fp64 record: {e}", file=sys.stderr)
         line = {
@@ -383,22 +577,33 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "batch_per_gpu": B, "pieces": N, "K": K, "S": S,
                        "kappa": int(prm.kappa), "mem_size": int(prm.mem_size), "past": int(prm.past),
-                       "delta": float(prm.delta),
+                       "delta": float(prm.delta), "mapping": mapping, "warm_start": a.warm_start,
                        "parallelism": f"problems block-partitioned over {world} rank(s)" +
-                                      (", one NCCL all-gather of coefficients per step" if world > 1 else ""),
-                       "l2": "inputs larger than L2 (half-planes %.0f MB per GPU per step), no flush" % (pb.hpolys.nbytes / 1e6)},
-            "evals_per_s": world * evals_sum * a.steps / (ms_tot * 1e-3),
+                                      (", one in-place NCCL all-gather of coefficients per step" if world > 1 else ""),
+                       "l2": "inputs larger than L2 (half-planes %.0f MB per GPU per step), no flush" % (pb.hpolys.nbytes / 1e6),
+                       "host": host_info()},
+            "evals_per_s": evals_all * a.steps / (ms_tot * 1e-3),
             "mean_evals_per_traj": evals_sum / B, "p95_evals_per_traj": float(np.percentile(evals_np, 95)),
             "mean_iters_per_traj": iters_mean, "ok_fraction": ok_frac, "status_hist": status_hist, "quality": quality,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": f"optimize_kernel<S={S}>", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": f"optimize_kernel<S={S}>", "kernel_ms": k_ms0,
                          "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
-                         "note": "algorithmic bytes = sum(evals)*bytes_eval + B*coeff bytes (SURVEY 8d); the persistent kernel keeps "
-                                 "a problem on chip for its ~420 evaluations, so DRAM traffic is ~230x lower; what bounds it is "
-                                 "fp64 latency and instruction supply (roofline_fp64, profiles/)"},
+                         "note": "algorithmic bytes = sum(evals)*bytes_eval + B*coeff bytes (SURVEY 8d), rank 0's launch; the persistent "
+                                 "kernel keeps a problem on chip for all of its evaluations, so DRAM traffic is ~230x lower; what bounds "
+                                 "it is fp64 latency and instruction supply (roofline_fp64, profiles/)"},
+            "step_breakdown_ms": {"optimize_kernel_max_over_ranks": k_ms, "optimize_kernel_min_over_ranks": float(ranks_ms[:, 0].min()),
+                                  "optimize_kernel_per_rank": [float(v) for v in ranks_ms[:, 0]],
+                                  "allgather_max_over_ranks": float(ranks_ms[:, 1].max()),
+                                  "allgather_per_rank": [float(v) for v in ranks_ms[:, 1]],
+                                  "note": "CUDA events on the launching stream; a rank's all-gather time includes waiting for the slowest "
+                                          "rank's kernel (the collective cannot finish before every rank has entered it)"},
             "gpu_launches": a.steps,
             "clocks": clk,
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if warm is not None:
+            line["warm_start"] = warm
         if fp64 is not None:
             line["roofline_fp64"] = fp64
         if evk is not None:
@@ -412,7 +617,7 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": thr, "kind": kind,
                                     "sample": f"first {sample} problems of the same seeded stream, {thr} threads; driver: {drv}",
                                     "evals_per_s": float(res["evals"].sum()) / dt,
-                                    "mean_evals_per_traj": float(res["evals"].mean())}
+                                    "mean_evals_per_traj": float(res["evals"].mean()), "host": host_info()}
         print(json.dumps(line), flush=True)
     mb.close()
     if world > 1:

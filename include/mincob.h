@@ -218,6 +218,10 @@ int mincob_gathered_device(mincob_handle h, const double **coeffs_all_d, int64_t
  *      C++ caller such as LearningPlanner needs no CUDA headers of its own. */
 int mincob_host_alloc(void **out, uint64_t bytes);
 int mincob_host_free(void *p);
+/*      ... and page-locking of memory the caller owns (cudaHostRegister / cudaHostUnregister), e.g. a shared-memory
+ *      segment mapped by all ranks of a node: every rank's results then land directly in the consumer's memory. */
+int mincob_host_register(void *p, uint64_t bytes);
+int mincob_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

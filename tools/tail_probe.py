@@ -6,7 +6,9 @@ sys.path.insert(0, '.')
 from allocnet_b200 import api, synth
 from allocnet_b200.params import default_params
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-pb = synth.make_problems(B, N=8, K=16, S=3)
+NP = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+KK = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+pb = synth.make_problems(B, N=NP, K=KK, S=3)
 mb = api.MincoBatch(default_params(3), device=0); mb.set_problems(pb)
 for rep in range(2):
     r = mb.optimize(pb.x0(), want_coeffs=False)
