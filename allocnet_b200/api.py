@@ -44,17 +44,21 @@ class MincobError(RuntimeError):
 
 
 _lib = None
+_libs = {}
 
 
-def load_library() -> C.CDLL:
-    """dlopen libmincob.so; raises (loudly) when it has not been built."""
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen libmincob.so (or another build of it, e.g. libmincob_strict.so); raises (loudly) when it has not been built."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise MincobError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    if path is not None and path in _libs:
+        return _libs[path]
+    lib_path = path or LIB_PATH
+    if not os.path.exists(lib_path):
+        raise MincobError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(lib_path)
     L.mincob_last_error.restype = C.c_char_p
     L.mincob_strerror.restype = C.c_char_p
     L.mincob_lbfgs_strerror.restype = C.c_char_p
@@ -94,7 +98,10 @@ def load_library() -> C.CDLL:
     L.mincob_max_rates_device.argtypes = [_vp, _vp, _vp, _vp]
     if hasattr(L, "mincob_last_mapping"):   # absent from older builds selected with MINCOB_LIBRARY (A/B runs)
         L.mincob_last_mapping.argtypes = [_vp, C.POINTER(C.c_int)]
-    _lib = L
+    if path is None:
+        _lib = L
+    else:
+        _libs[path] = L
     return L
 
 
@@ -118,8 +125,8 @@ def _dev_ptr(t):
 class MincoBatch:
     """Batched MINCO optimizer handle (one per GPU).  Mirrors GCOPTER_PolytopeSFC: setup -> optimize."""
 
-    def __init__(self, params: MincobParams | None = None, device: int = 0):
-        self.L = load_library()
+    def __init__(self, params: MincobParams | None = None, device: int = 0, lib_path: str | None = None):
+        self.L = load_library(lib_path)
         self.params = params if params is not None else default_params()
         self.h = _vp()
         rc = self.L.mincob_create(C.byref(self.h), C.byref(self.params), int(device))

@@ -78,5 +78,32 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+STRICT_LIB = os.path.join(HERE, "libmincob_strict.so")
+
+
+def build_strict_library(force: bool = False) -> str:
+    """The -DMINCOB_STRICT=1 variant (reference-form divisions / square roots in the L-BFGS decisions), S = 3 with 5 and 8
+    lanes only: a test artefact that the GPU parity suite compares the shipped build with."""
+    if not force and os.path.exists(STRICT_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(STRICT_LIB) for s in _sources()):
+        return STRICT_LIB
+    nvcc = _nvcc()
+    obj = OBJ + "_strict"
+    os.makedirs(obj, exist_ok=True)
+    jobs = []
+    for S, L in INST:
+        thr = THREADS.get(L, 128)
+        minb = MINB.get(S, 2) * 128 // thr
+        o = os.path.join(obj, f"kernels_s{S}_l{L}.o")
+        jobs.append(([nvcc, *ARCH, *FLAGS, "-DMINCOB_STRICT=1", f"-DMINCOB_S={S}", f"-DMINCOB_LPT={L}", f"-DMINCOB_MINB={minb}",
+                      f"-DMINCOB_THREADS={thr}", "-c", os.path.join(CSRC, "kernels_inst.cu"), "-o", o], o))
+    o = os.path.join(obj, "mincob.o")
+    jobs.append(([nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, "mincob.cu"), "-o", o], o))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        list(ex.map(lambda j: _run(j[0], j[1] + ".log"), jobs))
+    _run([nvcc, *ARCH, "-shared", "-o", STRICT_LIB, *[j[1] for j in jobs], "-ldl"], os.path.join(obj, "link.log"))
+    return STRICT_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_strict_library(force="--force" in sys.argv))

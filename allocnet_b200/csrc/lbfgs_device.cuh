@@ -27,6 +27,14 @@
 #ifndef MINCOB_HDEP
 #define MINCOB_HDEP 2   // (s, y) pairs of the two-loop recursion in flight ahead of their use (MEM > 0 kernels)
 #endif
+// MINCOB_STRICT: the decision arithmetic of gcopter/lbfgs.hpp written exactly as the reference writes it (quotients,
+// square roots, divisions by y.s) instead of the division-free forms of the default build, which are equal in exact
+// arithmetic but can round a decision differently within an ulp of a threshold.  build.py also builds this variant
+// (allocnet_b200/libmincob_strict.so); tests/test_gpu_parity.py::test_division_free_decisions_match_reference_forms
+// measures how often the two builds decide differently.
+#ifndef MINCOB_STRICT
+#define MINCOB_STRICT 0
+#endif
 #ifndef MINCOB_MINB
 #define MINCOB_MINB 2   // resident blocks per SM the optimize kernel is compiled for (register cap)
 #endif
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
         // |g|_inf and |x|_inf only feed the g_epsilon test (lbfgs.hpp:531, :600), which can never fire for g_epsilon = 0
         // (the default here and upstream): a warp-uniform branch then skips both reductions
         double gn = 1.0, xn = 1.0;
-        if (P.g_eps > 0.0) { gn = ginf<LPT>(FULL, g); xn = ginf<LPT>(FULL, x); }
+        if (MINCOB_STRICT || P.g_eps > 0.0) { gn = ginf<LPT>(FULL, g); xn = ginf<LPT>(FULL, x); }
         const double gg = gdot<LPT>(FULL, g, g);
         const double gd = gdot<LPT>(FULL, g, d);
         const int kslot = (past > 0) ? k % past : 0;   // slot of the `past` ring this iteration reads, then overwrites
@@ -343,10 +351,18 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             k = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) d[i] = -g[i];
+#if MINCOB_STRICT
+            if (gn / fmax(1.0, xn) < P.g_eps) {   // lbfgs.hpp:531 as written
+#else
             if (gn < P.g_eps * fmax(1.0, xn)) {   // gnorm / max(1, xnorm) < g_epsilon (lbfgs.hpp:531), without the fp64 division
+#endif
                 ret = LBFGS_CONVERGENCE; finish = 1;
             } else {
+#if MINCOB_STRICT
+                stp = 1.0 / sqrt(gg);           // step = 1.0 / d.norm() (lbfgs.hpp:543)
+#else
                 stp = rsqrt(gg);                // 1 / |g| (lbfgs.hpp:543), one rounding instead of two
+#endif
                 k = 1; end = 0; bound = 0;
                 start_ls = true;
             }
@@ -385,10 +401,18 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 for (int i = 0; i < 4; ++i) { x[i] = xp[i]; g[i] = gp[i]; }
                 ret = fail; finish = 1;
             } else if (done) {              // lbfgs.hpp:580-640
+#if MINCOB_STRICT
+                if (gn / fmax(1.0, xn) < P.g_eps) { ret = LBFGS_CONVERGENCE; finish = 1; }
+#else
                 if (gn < P.g_eps * fmax(1.0, xn)) { ret = LBFGS_CONVERGENCE; finish = 1; }
+#endif
                 if (!finish && past > 0) {
                     // |pf - fx| / max(1, |fx|) < delta (lbfgs.hpp:610-614) as a product: an fp64 division is ~35 instructions
+#if MINCOB_STRICT
+                    if (past <= k && fabs(pfk - fx) / fmax(1.0, fabs(fx)) < P.delta) { ret = LBFGS_STOP; finish = 1; }
+#else
                     if (past <= k && fabs(pfk - fx) < P.delta * fmax(1.0, fabs(fx))) { ret = LBFGS_STOP; finish = 1; }
+#endif
                     if (!finish) { write_pf = true; pf_slot = kslot; }
                 }
                 if (!finish && P.max_iter != 0 && P.max_iter <= k) { ret = LBFGSERR_MAXIMUMITERATION; finish = 1; }
@@ -404,7 +428,11 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
             for (int i = 0; i < 4; ++i) { sv[i] = x[i] - xp[i]; yv[i] = g[i] - gp[i]; }
             const double ys = gdot<LPT>(FULL, yv, sv), yy = gdot<LPT>(FULL, yv, yv);
             const double ss = gdot<LPT>(FULL, sv, sv), gpgp = gdot<LPT>(FULL, gp, gp);
+#if MINCOB_STRICT
+            const double iys = ys;         // keep y.s itself and divide where lbfgs.hpp:676-701 divides
+#else
             const double iys = 1.0 / ys;   // the two-loop recursion only ever divides by y.s
+#endif
             bool two = false;
             if (upd) {
                 ++k;
@@ -415,7 +443,11 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 for (int i = 0; i < 4; ++i) d[i] = -g[i];
                 if (lig == 0) ysv[end] = iys;
                 // ys > cautious * ss * |gp| (lbfgs.hpp:655), squared so that no fp64 square root is needed (the right side is >= 0)
+#if MINCOB_STRICT
+                two = ys > P.cautious * ss * sqrt(gpgp);       // lbfgs.hpp:655 as written
+#else
                 two = ys > 0.0 && ys * ys > (ss * P.cautious) * (ss * P.cautious) * gpgp;
+#endif
                 if (two) {
                     ++bound;
                     bound = m < bound ? m : bound;
@@ -439,7 +471,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                     if (i >= 1 && i + HDEP < MEM) hq[i + HDEP] = fetch_nth(i + HDEP);
                     const bool on = two && i < bound;
                     const double sj[4] = {hq[i].s.x, hq[i].s.y, hq[i].s.z, hq[i].s.w};
-                    const double aj = gdot<LPT>(FULL, sj, d) * hq[i].rys;
+                    const double aj = MINCOB_STRICT ? gdot<LPT>(FULL, sj, d) / hq[i].rys : gdot<LPT>(FULL, sj, d) * hq[i].rys;
                     al[i] = aj;
                     if (on) { d[0] -= aj * hq[i].y.x; d[1] -= aj * hq[i].y.y; d[2] -= aj * hq[i].y.z; d[3] -= aj * hq[i].y.w; }
                 }
@@ -456,7 +488,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                     const Pair &h = (i >= HKEEP || i == 0) ? hq[i] : hr[i];
                     const bool on = two && i < bound;
                     const double yj[4] = {h.y.x, h.y.y, h.y.z, h.y.w};
-                    const double beta = gdot<LPT>(FULL, yj, d) * h.rys;
+                    const double beta = MINCOB_STRICT ? gdot<LPT>(FULL, yj, d) / h.rys : gdot<LPT>(FULL, yj, d) * h.rys;
                     if (on) {
                         const double cf = al[i] - beta;
                         d[0] += cf * h.s.x; d[1] += cf * h.s.y; d[2] += cf * h.s.z; d[3] += cf * h.s.w;
@@ -488,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                     const Pair n2 = fetch(slot_at(i + 2 < nb ? i + 2 : nb - 1));
                     const int j = slot_at(i);
                     const double sj[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w};
-                    const double aj = gdot<LPT>(FULL, sj, d) * ysv[j];
+                    const double aj = MINCOB_STRICT ? gdot<LPT>(FULL, sj, d) / ysv[j] : gdot<LPT>(FULL, sj, d) * ysv[j];
                     if (on) {
                         if (lig == 0) alpha[j] = aj;
                         d[0] -= aj * cur.y.x; d[1] -= aj * cur.y.y; d[2] -= aj * cur.y.z; d[3] -= aj * cur.y.w;
@@ -511,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                     const Pair n2 = fetch(fwd_at(i + 2));
                     const int j = fwd_at(i);
                     const double yj[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
-                    const double beta = gdot<LPT>(FULL, yj, d) * ysv[j];
+                    const double beta = MINCOB_STRICT ? gdot<LPT>(FULL, yj, d) / ysv[j] : gdot<LPT>(FULL, yj, d) * ysv[j];
                     if (on) {
                         const double cf = alpha[j] - beta;
                         d[0] += cf * cur.s.x; d[1] += cf * cur.s.y; d[2] += cf * cur.s.z; d[3] += cf * cur.s.w;

@@ -38,6 +38,9 @@
 #ifndef MINCOB_JB
 #define MINCOB_JB 6          // samples whose positions phase 1 of penalty_piece holds in registers at once
 #endif
+#ifndef MINCOB_UNROLL_KG
+#define MINCOB_UNROLL_KG 2   // same, when the rows are read from global memory (polytopes too large to stage)
+#endif
 #ifndef MINCOB_UNROLL_K
 #define MINCOB_UNROLL_K 1    // half-plane rows per trip of the phase-1 loop (2: -4 %, 4: -4 %, 8: -10 %; the kernel is code-size sensitive)
 #endif
@@ -582,7 +585,9 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                     pos[jj][x] = v;
                 }
             }
-            constexpr int UK = MINCOB_UNROLL_K;
+            // rows in shared memory: one per trip (code size); rows in global memory (K too large to stage): several
+            // loads in flight per trip, the L2 latency is what that loop waits for
+            constexpr int UK = PSMEM ? MINCOB_UNROLL_K : MINCOB_UNROLL_KG;
 #pragma unroll 1
             for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
                 unsigned pm = 0u;

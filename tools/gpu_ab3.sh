@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out; : > gpurun_out/ab3.log
+run() { lib=$1; shift; echo -n "$lib :: $* :: " | tee -a gpurun_out/ab3.log
+  MINCOB_LIBRARY=$lib timeout 600 python bench.py "$@" --no-cpu --no-e2e --no-check 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['roofline']['kernel_ms'],2), d['clocks']['sm_mhz'])" | tee -a gpurun_out/ab3.log; }
+for lib in "" $(ls variants/*.so 2>/dev/null | grep -v timing); do
+  run "$lib" --pieces 5 --K 50 --steps 3 --warmup 3
+  run "$lib" --pieces 8 --K 40 --steps 3 --warmup 3
+done
