@@ -130,7 +130,12 @@ def make_problems(B: int, N: int = 8, K: int = 16, S: int = 3, *, seed: int = SE
     hrows = np.zeros((B, N), dtype=np.int32)
 
     for i in range(N):
-        k0 = 64 + 128 * i
+        # draw indices of piece i: [k0, k0 + stride).  Up to 40 rows the plane draws (k0+16 .. k0+16+3(K-6)) and the ragged-row
+        # draw stay inside 128 indices (and the committed fixtures depend on that numbering); above, a wider stride keeps
+        # neighbouring pieces' draws disjoint
+        stride = 128 if K <= 40 else 512
+        k0 = 64 + stride * i
+        ragged_at = k0 + (120 if K <= 40 else 500)
         if i > 0:  # rotate the previous direction by at most 60 degrees
             r = dr.sphere(k0 + 1)
             theta = dr.uniform(k0 + 3, 0.0, np.pi / 3.0)
@@ -169,7 +174,7 @@ def make_problems(B: int, N: int = 8, K: int = 16, S: int = 3, *, seed: int = SE
             hpolys[:, i, :K] = np.stack(rows, axis=1)
             hrows[:, i] = K
             if ragged_rows:
-                keep = np.minimum(K, min(6, K) + np.floor(dr.u(k0 + 120) * (K - min(6, K) + 1)).astype(np.int32))
+                keep = np.minimum(K, min(6, K) + np.floor(dr.u(ragged_at) * (K - min(6, K) + 1)).astype(np.int32))
                 hrows[:, i] = keep
                 mask = np.arange(K)[None, :] >= keep[:, None]
                 hpolys[:, i, :K][mask] = 0.0

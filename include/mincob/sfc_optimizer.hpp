@@ -6,10 +6,13 @@
 //       k = 0 highest power) as the call it replaces:
 //           qp_solver.solve(iniPVA, finPVA, hPolys, times, flatten_coffmats)
 //           src/planner/include/planner/learning_planner.hpp:196   (consumer :201-233)
-//       with one difference that is the point of the exercise: `times` is in/out.  The net's time
-//       allocation is the WARM START of a spatial-temporal optimisation (lbfgs_optimize on the
-//       GCOPTER costFunctional, on the GPU), and the optimised durations are written back so that
-//       `jerk_traj.emplace_back(times(i), coffMat)` at :216 builds the optimised trajectory.
+//       Two time modes (last argument):
+//         TimeMode::Fixed (default)  the literal replacement: the network's durations are DATA, exactly as in the
+//             incumbent QP (qp_solver.hpp:119-360 keeps `times` fixed); only the waypoints are optimised
+//             (MINCOB_FLAG_FREEZE_TIMES) and `times` is not written.
+//         TimeMode::Optimize         `times` is in/out: the net's allocation is the WARM START of the spatial-temporal
+//             optimisation (upstream GCOPTER behaviour) and the optimised durations are written back, so that
+//             `jerk_traj.emplace_back(times(i), coffMat)` at :216 builds the optimised trajectory.
 //
 //   mincob::PolytopeSFC   setup(...) / optimize(...) / static costFunctional(void*, x, g)
 //       the upstream GCOPTER_PolytopeSFC shape: `costFunctional` has the
@@ -20,8 +23,9 @@
 //
 //   mincob::BatchOptimizer   B problems at once (host pointers in the layouts of include/mincob.h).
 //
-// Half-plane sign: the planner hands rows [n, b] with n.p <= b (learning_planner.hpp:293-299); the
-// library wants GCOPTER's n.p + d <= 0 (geo_utils.hpp:41-42), so column 3 is negated on the way in.
+// Half-plane sign: the planner hands rows [n, b] with n.p <= b (learning_planner.hpp:293-299); they are passed on
+// unchanged with MINCOB_FLAG_PLANNER_ROWS set (GCOPTER's own n.p + d <= 0 form, geo_utils.hpp:41-42, is the
+// library's default for callers that come from sfc_gen / firi directly).
 // ============================================================================
 #pragma once
 #include <Eigen/Eigen>
@@ -72,6 +76,7 @@ public:
         N = (int)hPolys.size();
         if (N < 1 || N > MINCOB_MAX_PIECES) return false;
         if (params) prm = *params; else mincob_default_params(&prm, 3);
+        prm.flags |= MINCOB_FLAG_PLANNER_ROWS;                  // hPolys rows are [n, b], n.p <= b
         const int S = prm.S;
         if (!h && mincob_create(&h, &prm, device) != 0) return false;
         if (mincob_set_params(h, &prm) != 0) return false;
@@ -86,7 +91,7 @@ public:
             rows[i] = (int)hPolys[i].rows();
             for (int r = 0; r < rows[i]; ++r) {
                 double *o = &planes[((size_t)i * K + r) * 4];
-                o[0] = hPolys[i](r, 0); o[1] = hPolys[i](r, 1); o[2] = hPolys[i](r, 2); o[3] = -hPolys[i](r, 3);
+                o[0] = hPolys[i](r, 0); o[1] = hPolys[i](r, 1); o[2] = hPolys[i](r, 2); o[3] = hPolys[i](r, 3);
             }
         }
         n = N + 3 * (N - 1);
@@ -142,20 +147,27 @@ private:
     std::vector<int32_t> rows;
 };
 
+enum class TimeMode { Fixed, Optimize };
+
 // Drop-in for qp_solver.solve at learning_planner.hpp:196 (see the header comment).
 template <class MatPVA, class Polys, class Times>
 inline bool solve(const MatPVA &iniPVA, const MatPVA &finPVA, const Polys &hPolys, Times &times,
                   Eigen::VectorXd &flat_coeffs, const Eigen::Matrix3Xd *inPs0 = nullptr,
-                  const mincob_params *params = nullptr) {
+                  const mincob_params *params = nullptr, TimeMode mode = TimeMode::Fixed) {
     static PolytopeSFC sfc;   // LearningPlanner is single-threaded and not re-entrant
-    if (!sfc.setup(iniPVA, finPVA, hPolys, times, inPs0, params)) return false;
+    mincob_params p;
+    if (params) p = *params; else mincob_default_params(&p, 3);
+    if (mode == TimeMode::Fixed) p.flags |= MINCOB_FLAG_FREEZE_TIMES; else p.flags &= ~MINCOB_FLAG_FREEZE_TIMES;
+    if (!sfc.setup(iniPVA, finPVA, hPolys, times, inPs0, &p)) return false;
     int status = 0;
     sfc.optimize(&status);
     if (status < 0 && status != -1008 /* LBFGSERR_MAXIMUMITERATION: best iterate is still usable */) return false;
     flat_coeffs.resize((int)sfc.coeffs.size());
     for (size_t i = 0; i < sfc.coeffs.size(); ++i) flat_coeffs((int)i) = sfc.coeffs[i];
-    typedef typename std::decay<decltype(times(0))>::type TimeScalar;   // float for the net's VectorXf
-    for (int i = 0; i < sfc.N; ++i) times(i) = (TimeScalar)sfc.durations[i];
+    if (mode == TimeMode::Optimize) {
+        typedef typename std::decay<decltype(times(0))>::type TimeScalar;   // float for the net's VectorXf
+        for (int i = 0; i < sfc.N; ++i) times(i) = (TimeScalar)sfc.durations[i];
+    }
     return true;
 }
 

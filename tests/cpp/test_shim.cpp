@@ -99,7 +99,15 @@ int main(int argc, char **argv) {
         dump("dev_x", sfc.x); dump("dev_coeffs", sfc.coeffs); dump("dev_T", sfc.durations);
         // 5. the one-line replacement of qp_solver.solve (learning_planner.hpp:196); q0 by projection
         Eigen::VectorXd flat;
-        const bool ok = mincob::solve(ini, fin, hPolys, times, flat);
+        {   // 5a. literal replacement: durations fixed, `times` untouched
+            Eigen::VectorXd flat_fixed;
+            const bool okf = mincob::solve(ini, fin, hPolys, times, flat_fixed);
+            std::printf("\"solvefix_ok\": %s,\n", okf ? "true" : "false");
+            v.clear(); for (int i = 0; i < N; ++i) v.push_back((double)times(i)); dump("solvefix_times", v);
+            v.clear(); for (int i = 0; i < flat_fixed.size(); ++i) v.push_back(flat_fixed(i)); dump("solvefix_flat", v);
+        }
+        // 5b. durations refined as well (times in/out)
+        const bool ok = mincob::solve(ini, fin, hPolys, times, flat, nullptr, nullptr, mincob::TimeMode::Optimize);
         std::printf("\"solve_ok\": %s,\n", ok ? "true" : "false");
         v.clear(); for (int i = 0; i < N; ++i) v.push_back((double)times(i)); dump("solve_times", v);
         v.clear(); for (int i = 0; i < flat.size(); ++i) v.push_back(flat(i)); dump("solve_flat", v, false);

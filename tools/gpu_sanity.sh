@@ -7,8 +7,10 @@ import numpy as np, sys
 sys.path.insert(0, '.')
 from allocnet_b200 import api, synth
 from allocnet_b200.params import default_params
-for S, N, K, B in ((3, 8, 16, 96), (3, 5, 50, 40), (4, 8, 16, 40), (3, 16, 16, 24), (3, 1, 4, 8)):
-    prm = default_params(S, max_iterations=12)
+from allocnet_b200 import params as P
+for S, N, K, B, mp in ((3, 8, 16, 96, P.MAP_THROUGHPUT), (3, 8, 16, 9, P.MAP_LATENCY), (3, 5, 50, 40, P.MAP_THROUGHPUT), (3, 5, 16, 13, P.MAP_LATENCY),
+                       (3, 3, 7, 31, P.MAP_THROUGHPUT), (4, 8, 16, 40, P.MAP_THROUGHPUT), (4, 5, 16, 7, P.MAP_LATENCY), (3, 16, 16, 24, P.MAP_LATENCY), (3, 1, 4, 8, P.MAP_AUTO)):
+    prm = default_params(S, max_iterations=12, mapping=mp)
     pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=(K == 50))
     mb = api.MincoBatch(prm, device=0); mb.set_problems(pb)
     f, g = mb.evaluate(pb.x0()); r = mb.optimize(pb.x0())
@@ -19,4 +21,3 @@ for S, N, K, B in ((3, 8, 16, 96), (3, 5, 50, 40), (4, 8, 16, 40), (3, 16, 16, 2
 PY
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck.log
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python /tmp/san.py > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
