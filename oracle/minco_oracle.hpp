@@ -133,6 +133,21 @@ inline void basis(double t, int d, double *out) {
         out[k] = f * tp;
     }
 }
+// rows d = 0..ND-1 of the derivative basis at t from ONE table of powers: pw[k] is built by the same repeated
+// multiplication as in basis(), so every entry has the same bits; the factors k!/(k-d)! are exact small integers.
+template <int D, int ND>
+inline void basis_rows(double t, double (&out)[ND][D]) {
+    double pw[D];
+    pw[0] = 1.0;
+    for (int k = 1; k < D; ++k) pw[k] = pw[k - 1] * t;
+    for (int d = 0; d < ND; ++d)
+        for (int k = 0; k < D; ++k) {
+            if (k < d) { out[d][k] = 0.0; continue; }
+            double f = 1.0;
+            for (int u = 0; u < d; ++u) f *= static_cast<double>(k - u);
+            out[d][k] = f * pw[k - d];
+        }
+}
 inline double factorial(int d) {
     double f = 1.0;
     for (int u = 2; u <= d; ++u) f *= u;
@@ -209,13 +224,20 @@ public:
     int pieces() const { return N; }
 
     // E = sum_i int_0^Ti |p^(S)|^2 dt  (no 1/2).
+    // T^e, e = 0 .. 2S-1, by repeated multiplication (the timed CPU path should not pay for std::pow)
+    static void tpowers(double t, double (&tp)[D]) {
+        tp[0] = 1.0;
+        for (int e = 1; e < D; ++e) tp[e] = tp[e - 1] * t;
+    }
     void getEnergy(double &energy) const {
         energy = 0.0;
+        double tp[D];
         for (int i = 0; i < N; ++i) {
+            tpowers(T[i], tp);
             for (int a = S; a < D; ++a)
                 for (int c = S; c < D; ++c) {
                     const int e = a + c - 2 * S + 1;
-                    const double m = fallfac(a) * fallfac(c) * std::pow(T[i], e) / e;
+                    const double m = fallfac(a) * fallfac(c) * tp[e] / e;
                     energy += m * dot3(&b[(D * i + a) * 3], &b[(D * i + c) * 3]);
                 }
         }
@@ -223,23 +245,28 @@ public:
     // gdC: (2S*N) x 3 row-major, OVERWRITTEN.
     void getEnergyPartialGradByCoeffs(double *gdC) const {
         std::fill(gdC, gdC + static_cast<size_t>(D) * N * 3, 0.0);
-        for (int i = 0; i < N; ++i)
+        double tp[D];
+        for (int i = 0; i < N; ++i) {
+            tpowers(T[i], tp);
             for (int a = S; a < D; ++a)
                 for (int c = S; c < D; ++c) {
                     const int e = a + c - 2 * S + 1;
-                    const double m = 2.0 * fallfac(a) * fallfac(c) * std::pow(T[i], e) / e;
+                    const double m = 2.0 * fallfac(a) * fallfac(c) * tp[e] / e;
                     for (int x = 0; x < 3; ++x)
                         gdC[(D * i + a) * 3 + x] += m * b[(D * i + c) * 3 + x];
                 }
+        }
     }
     // gdT: N, OVERWRITTEN.
     void getEnergyPartialGradByTimes(double *gdT) const {
+        double tp[D];
         for (int i = 0; i < N; ++i) {
             double g = 0.0;
+            tpowers(T[i], tp);
             for (int a = S; a < D; ++a)
                 for (int c = S; c < D; ++c) {
                     const int e = a + c - 2 * S + 1;
-                    const double m = fallfac(a) * fallfac(c) * std::pow(T[i], e - 1);
+                    const double m = fallfac(a) * fallfac(c) * tp[e - 1];
                     g += m * dot3(&b[(D * i + a) * 3], &b[(D * i + c) * 3]);
                 }
             gdT[i] = g;
@@ -356,7 +383,8 @@ inline void attach_penalty(const PenaltyParams &pp, const Problem &pb, const dou
                            const double *coeffs, double &cost, double *gdT, double *gdC) {
     constexpr int D = 2 * S;
     const int N = pb.N, kap = pp.kappa;
-    double b0[D], b1[D], b2[D], b3[D], b4[D];
+    double bb[5][D];
+    double (&b0)[D] = bb[0], (&b1)[D] = bb[1], (&b2)[D] = bb[2], (&b3)[D] = bb[3], (&b4)[D] = bb[4];
     const double vmax2 = pp.v_max * pp.v_max, amax2 = pp.a_max * pp.a_max, jmax2 = pp.j_max * pp.j_max;
     for (int i = 0; i < N; ++i) {
         const double *c = coeffs + static_cast<size_t>(D) * i * 3;
@@ -365,8 +393,7 @@ inline void attach_penalty(const PenaltyParams &pp, const Problem &pb, const dou
         const double *hp = pb.hpolys ? pb.hpolys + static_cast<size_t>(i) * pb.Kstride * 4 : nullptr;
         for (int j = 0; j <= kap; ++j) {
             const double s = j * step;
-            basis<D>(s, 0, b0); basis<D>(s, 1, b1); basis<D>(s, 2, b2);
-            basis<D>(s, 3, b3); basis<D>(s, 4, b4);
+            basis_rows<D, 5>(s, bb);
             double pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, acc[3] = {0, 0, 0}, jer[3] = {0, 0, 0}, sna[3] = {0, 0, 0};
             for (int k = 0; k < D; ++k)
                 for (int a = 0; a < 3; ++a) {
@@ -378,29 +405,35 @@ inline void attach_penalty(const PenaltyParams &pp, const Problem &pb, const dou
             const double alpha = static_cast<double>(j) / kap;
             double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
             double f, df;
+            bool any_active = false;
             for (int k = 0; k < K; ++k) {
                 const double *h = hp + k * 4;
                 const double viol = h[0] * pos[0] + h[1] * pos[1] + h[2] * pos[2] + (pp.planner_rows ? -h[3] : h[3]);
                 if (smoothed_l1(pp.mu, viol, f, df)) {
+                    any_active = true;
                     for (int a = 0; a < 3; ++a) gP[a] += pp.w_pos * df * h[a];
                     pena += pp.w_pos * f;
                 }
             }
             const double vv = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - vmax2;
             if (smoothed_l1(pp.mu, vv, f, df)) {
+                any_active = true;
                 for (int a = 0; a < 3; ++a) gV[a] += pp.w_vel * df * 2.0 * vel[a];
                 pena += pp.w_vel * f;
             }
             const double aa = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] - amax2;
             if (smoothed_l1(pp.mu, aa, f, df)) {
+                any_active = true;
                 for (int a = 0; a < 3; ++a) gA[a] += pp.w_acc * df * 2.0 * acc[a];
                 pena += pp.w_acc * f;
             }
             const double jj = jer[0] * jer[0] + jer[1] * jer[1] + jer[2] * jer[2] - jmax2;
             if (smoothed_l1(pp.mu, jj, f, df)) {
+                any_active = true;
                 for (int a = 0; a < 3; ++a) gJ[a] += pp.w_jerk * df * 2.0 * jer[a];
                 pena += pp.w_jerk * f;
             }
+            if (!any_active) continue;   // nothing violated at this sample: every term below is an exact zero
             const double w = node * step;
             for (int k = 0; k < D; ++k)
                 for (int a = 0; a < 3; ++a)
