@@ -38,6 +38,9 @@
 #ifndef MINCOB_JB
 #define MINCOB_JB 6          // samples whose positions phase 1 of penalty_piece holds in registers at once
 #endif
+#ifndef MINCOB_PLANE_PREFETCH
+#define MINCOB_PLANE_PREFETCH 1   // +1 % (N = 8) ... +3 % (N = 5): profiles/r02_ab.log
+#endif
 #ifndef MINCOB_UNROLL_KG
 #define MINCOB_UNROLL_KG 2   // same, when the rows are read from global memory (polytopes too large to stage)
 #endif
@@ -569,7 +572,9 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
         unsigned hit = 0u, pm0 = 0u, pm1 = 0u;
         {
             // sign-bit test: keep[jj] stays negative only while every n.p + d is negative; a sample
-            // with any value >= +0 is flagged and re-tested exactly (v > 0) in phase 2.
+            // with any value >= +0 is flagged and re-tested exactly (v > 0) in phase 2.  (Dropping the per-sample masks and
+            // working the flagged samples out of the flagged rows afterwards executes fewer instructions and is 2-3 %
+            // slower: profiles/r02_ab.log.)
             int keep[JB];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) keep[jj] = -1;
@@ -592,9 +597,18 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
                 unsigned pm = 0u;
                 const int k1 = min(K, k0 + 32);
+#if MINCOB_PLANE_PREFETCH
+                // software pipelining by one row: the next row's load is in flight while this row's tests issue
+                Plane hnext = load_plane<PSMEM>(planes + (size_t)(k0 < k1 ? k0 : 0) * rstride);
+#endif
 #pragma unroll UK
                 for (int k = k0; k < k1; ++k) {
+#if MINCOB_PLANE_PREFETCH
+                    const Plane h = hnext;
+                    hnext = load_plane<PSMEM>(planes + (size_t)(k + 1 < k1 ? k + 1 : k) * rstride);
+#else
                     const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+#endif
                     int all = -1;
 #pragma unroll
                     for (int jj = 0; jj < JB; ++jj) {
