@@ -35,7 +35,7 @@ SYMBOLS = [
     "mincob_check_feasibility", "mincob_check_feasibility_device", "mincob_measure_fp64_peak",
     "mincob_max_rates", "mincob_max_rates_device", "mincob_minco_forward_device", "mincob_minco_propagate_device",
     "mincob_optimize_sharded_local", "mincob_gathered_device", "mincob_last_mapping", "mincob_host_register",
-    "mincob_host_unregister",
+    "mincob_host_unregister", "mincob_set_problems_async",
 ]
 
 
@@ -70,6 +70,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     L.mincob_last_error.argtypes = [_vp]
     L.mincob_set_problems.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
     L.mincob_set_problems_device.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
+    if hasattr(L, "mincob_set_problems_async"):
+        L.mincob_set_problems_async.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
     L.mincob_evaluate.argtypes = [_vp, _vp, _vp, _vp]
     L.mincob_evaluate_device.argtypes = [_vp, _vp, _vp, _vp]
     L.mincob_optimize.argtypes = [_vp] + [_vp] * 7
@@ -202,6 +204,18 @@ class MincoBatch:
         hp = self._want(_f64(pb.hpolys), (B, N, K, 4), "hpolys") if K > 0 else None
         hr = self._want(np.ascontiguousarray(pb.hrows, dtype=np.int32), (B, N), "hrows") if K > 0 else None
         self._check(self.L.mincob_set_problems(self.h, B, N, K, _np_ptr(head), _np_ptr(tail), _np_ptr(hp), _np_ptr(hr)))
+        self.B, self.N, self.K = B, N, K
+
+    def set_problems_async(self, pb):
+        """set_problems without waiting: pb's arrays must be page-locked, C-contiguous fp64 / int32 in the C-ABI layouts
+        (pinned_empty) and untouched until the next optimize call has returned; that call overlaps the upload."""
+        B, N, K, S = int(pb.B), int(pb.N), int(pb.K), self.S
+        for name, a, shape, dt in (("head", pb.head, (B, S, 3), np.float64), ("tail", pb.tail, (B, S, 3), np.float64)) + \
+                ((("hpolys", pb.hpolys, (B, N, K, 4), np.float64), ("hrows", pb.hrows, (B, N), np.int32)) if K > 0 else ()):
+            if a.dtype != dt or not a.flags.c_contiguous or tuple(a.shape) != shape:
+                raise MincobError(f"{name} must be a C-contiguous {np.dtype(dt).name} array of shape {shape}")
+        self._check(self.L.mincob_set_problems_async(self.h, B, N, K, _np_ptr(pb.head), _np_ptr(pb.tail),
+                                                     _np_ptr(pb.hpolys if K > 0 else None), _np_ptr(pb.hrows if K > 0 else None)))
         self.B, self.N, self.K = B, N, K
 
     def set_problems_device(self, B, N, K, head, tail, hpolys=None, hrows=None):

@@ -53,6 +53,7 @@ struct BatchArgs {
     double *x, *coeffs, *T;
     int *status, *iters, *evals;
     int *counter;               // work queue head
+    const int *ready;           // optional: problems [0, *ready) have arrived in device memory (chunked upload in flight)
     double *hist;               // optimize: (s, y) history scratch, one slab per resident group
     double *mult;               // optimize: block-solve multiplier scratch, one slab per resident block
     double *lpark;              // optimize: parked xp/gp/d, one slab per resident block

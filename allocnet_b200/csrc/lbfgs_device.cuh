@@ -212,6 +212,13 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                 if (want && lig == 0) p = atomicAdd(a.counter, 1);
                 p = group_first<LPT>(FULL, p);
             }
+            if (a.ready != nullptr) {
+                // the batch is still being uploaded in problem order (mincob_set_problems_async): wait for this problem
+                if (want && p < a.B) {
+                    while (*(volatile const int *)a.ready <= p) __nanosleep(200);
+                }
+                __syncwarp();
+            }
             if (want) {
                 if (p >= a.B) {
 #ifdef MINCOB_TIMING

@@ -71,7 +71,16 @@ struct mincob_ctx {
     mincob_params prm;
     DevParams dp;
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_copy0 = nullptr;
+    int *ready = nullptr;        // device: problems uploaded so far (mincob_set_problems_async)
+    int *ready_host = nullptr;   // pinned: the values written to `ready`, one per chunk
+    bool upload_in_flight = false;
+    // mincob_set_problems_async only records the request; the copies are enqueued by the next call that needs the data,
+    // so that an optimize call can put its own (small) x upload in front of them in the copy queue
+    bool upload_pending = false;
+    const double *p_head = nullptr, *p_tail = nullptr, *p_hpolys = nullptr;
+    const int32_t *p_hrows = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0, last_mapping = 0;
     bool timed = false;
@@ -212,10 +221,55 @@ static int do_minco(mincob_ctx *h, const MincoArgs &a, int propagate) {
     return launched(h, table_for(h->prm.S, a.N)->minco(h->stream, h->sm_count, a, propagate), "minco_kernel");
 }
 
-static int have_problems(mincob_ctx *h) {
+// Enqueue a recorded mincob_set_problems_async request on the copy stream: first `x_host` -> `x_dev` when the caller is a
+// host-pointer optimize call (its start vector must arrive BEFORE the bulk of the batch, the copy queue is first in first
+// out), then the arrival counter reset, then the batch in problem order, a counter update after every chunk.
+static int start_upload(mincob_ctx *h, const double *x_host = nullptr, double *x_dev = nullptr, size_t x_bytes = 0) {
+    if (!h->upload_pending) return 0;
+    h->upload_pending = false;
+    const int B = h->B, N = h->N, K = h->K, S = h->prm.S;
+    const size_t pb = (size_t)S * 3 * sizeof(double), pp = (size_t)N * K * 4 * sizeof(double), pr = (size_t)N * sizeof(int);
+    // the copy stream starts after whatever the compute stream has queued so far (a previous kernel may still read the buffers)
+    CU(h, cudaEventRecord(h->ev_copy, h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+    if (x_host) CU(h, cudaMemcpyAsync(x_dev, x_host, x_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(h, cudaMemsetAsync(h->ready, 0, sizeof(int), h->copy_stream));
+    CU(h, cudaEventRecord(h->ev_copy0, h->copy_stream));      // the optimize kernel must not start before x is there and the counter is reset
+    // chunk = a multiple of 4096 problems: no 128-byte line of head / tail / hrows / hpolys straddles two chunks, so a line
+    // an SM has cached never holds problems that had not arrived when it was read
+    int per = 4096;
+    while ((B + per - 1) / per > 4096) per *= 2;
+    for (int c = 0, lo = 0; lo < B; ++c, lo += per) {
+        const int cnt = (lo + per <= B) ? per : B - lo;
+        CU(h, cudaMemcpyAsync((char *)h->b_head.p + pb * lo, (const char *)h->p_head + pb * lo, pb * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaMemcpyAsync((char *)h->b_tail.p + pb * lo, (const char *)h->p_tail + pb * lo, pb * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        if (K > 0) {
+            CU(h, cudaMemcpyAsync((char *)h->b_hpolys.p + pp * lo, (const char *)h->p_hpolys + pp * lo, pp * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+            CU(h, cudaMemcpyAsync((char *)h->b_hrows.p + pr * lo, (const char *)h->p_hrows + pr * lo, pr * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        h->ready_host[c] = lo + cnt;
+        CU(h, cudaMemcpyAsync(h->ready, h->ready_host + c, sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    CU(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->upload_in_flight = true;
+    return 0;
+}
+
+// every consumer of the problem buffers other than the optimize kernel waits for the whole upload
+static int upload_done(mincob_ctx *h) {
+    int rc = start_upload(h);
+    if (rc) return rc;
+    if (h->upload_in_flight) {
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        h->upload_in_flight = false;
+    }
+    return 0;
+}
+// may_overlap: the caller (the optimize kernel) follows a chunked upload problem by problem; everybody else waits for it
+static int have_problems(mincob_ctx *h, bool may_overlap = false) {
     if (!h) return MINCOB_E_INVALID;
     if (h->B <= 0 || !h->head || !h->tail) return fail(h, MINCOB_E_STATE, "set_problems has not been called");
-    return 0;
+    return may_overlap ? 0 : upload_done(h);
 }
 static BatchArgs base_args(mincob_ctx *h) {
     BatchArgs a;
@@ -223,6 +277,7 @@ static BatchArgs base_args(mincob_ctx *h) {
     a.B = h->B; a.N = h->N; a.K = h->K;
     a.head = h->head; a.tail = h->tail; a.hpolys = h->hpolys; a.hrows = h->hrows;
     a.counter = h->counter; a.total_evals = h->total_evals;
+    a.ready = nullptr;
     return a;
 }
 
@@ -306,6 +361,14 @@ int mincob_create(mincob_handle *out, const mincob_params *params, int device) {
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&h->ready, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc((void **)&h->ready_host, 4096 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        mincob_destroy(h);
+        return MINCOB_E_ALLOC;
+    }
     if (cudaMalloc((void **)&h->counter, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void **)&h->total_evals, 128 * sizeof(unsigned long long)) != cudaSuccess) {
         mincob_destroy(h);
@@ -327,6 +390,11 @@ int mincob_destroy(mincob_handle h) {
     if (h->total_evals) cudaFree(h->total_evals);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ready) cudaFree(h->ready);
+    if (h->ready_host) cudaFreeHost(h->ready_host);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -395,6 +463,7 @@ int mincob_set_problems_device(mincob_handle h, int B, int N, int K, const doubl
     if (rc) return rc;
     if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
     if (hpolys && ((uintptr_t)hpolys & 31u)) return fail(h, MINCOB_E_INVALID, "hpolys must be 32-byte aligned");
+    if ((rc = upload_done(h))) return rc;
     if (K > 0 && (h->prm.flags & MINCOB_FLAG_PLANNER_ROWS)) {
         // the kernels read GCOPTER-sign rows: keep a converted copy (in place when the rows already are our staging copy)
         ON_DEVICE(h);
@@ -422,6 +491,7 @@ int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head
     if (rc) return rc;
     if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
     ON_DEVICE(h);
+    if ((rc = upload_done(h))) return rc;
     const int S = h->prm.S;
     const size_t nb = (size_t)B * S * 3 * sizeof(double), np = (size_t)B * N * K * 4 * sizeof(double),
                  nr = (size_t)B * N * sizeof(int);
@@ -438,6 +508,33 @@ int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head
                                     K > 0 ? (const int32_t *)h->b_hrows.p : nullptr);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->stream));   // host-pointer contract: the caller's buffers are free again on return
+    return 0;
+}
+
+// Upload in problem order, in chunks, on a second stream; after each chunk a counter in device memory says how many
+// problems have arrived.  The next mincob_optimize* call starts at once and its work queue waits per problem for that
+// counter, so the kernel overlaps all but the first chunk of the upload.  The caller's buffers must be page-locked
+// (mincob_host_alloc / mincob_host_register) and stay untouched until that optimize call has returned (host-pointer
+// form) or the stream has been synchronised.
+int mincob_set_problems_async(mincob_handle h, int B, int N, int K, const double *head, const double *tail,
+                              const double *hpolys, const int32_t *hrows) {
+    if (!h || !head || !tail) return MINCOB_E_INVALID;
+    int rc = check_shape(h, B, N, K);
+    if (rc) return rc;
+    if (K > 0 && (!hpolys || !hrows)) return fail(h, MINCOB_E_INVALID, "K > 0 needs hpolys and hrows");
+    if (h->prm.flags & MINCOB_FLAG_PLANNER_ROWS) return mincob_set_problems(h, B, N, K, head, tail, hpolys, hrows);   // needs the conversion pass
+    ON_DEVICE(h);
+    if ((rc = upload_done(h))) return rc;                      // a previous asynchronous batch is uploaded / consumed first
+    const int S = h->prm.S;
+    const size_t pb = (size_t)S * 3 * sizeof(double), pp = (size_t)N * K * 4 * sizeof(double), pr = (size_t)N * sizeof(int);
+    if ((rc = ensure(h, h->b_head, pb * B)) || (rc = ensure(h, h->b_tail, pb * B))) return rc;
+    if (K > 0 && ((rc = ensure(h, h->b_hpolys, pp * B)) || (rc = ensure(h, h->b_hrows, pr * B)))) return rc;
+    h->p_head = head; h->p_tail = tail; h->p_hpolys = hpolys; h->p_hrows = hrows;
+    h->upload_pending = true;
+    h->B = B; h->N = N; h->K = K;
+    h->head = (const double *)h->b_head.p; h->tail = (const double *)h->b_tail.p;
+    h->hpolys = K > 0 ? (const double *)h->b_hpolys.p : nullptr;
+    h->hrows = K > 0 ? (const int *)h->b_hrows.p : nullptr;
     return 0;
 }
 
@@ -479,7 +576,7 @@ static __global__ void fill_status_kernel(int *status, int B, int code) {
 
 int mincob_optimize_device(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
                            double *coeffs, double *T) {
-    int rc = have_problems(h);
+    int rc = have_problems(h, true);
     if (rc) return rc;
     if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
     ON_DEVICE(h);
@@ -497,6 +594,11 @@ int mincob_optimize_device(mincob_handle h, double *x, double *f, int32_t *statu
     if (h->prm.past > MINCOB_MAX_PAST) return fail(h, MINCOB_E_INVALID, "past > %d not supported", MINCOB_MAX_PAST);
     BatchArgs a = base_args(h);
     a.x = x; a.f_out = f; a.status = status; a.iters = iters; a.evals = evals; a.coeffs = coeffs; a.T = T;
+    if ((rc = start_upload(h))) return rc;   // x is already on the device: just get the batch moving
+    if (h->upload_in_flight) {          // chunked upload: start as soon as the arrival counter has been reset
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_copy0, 0));
+        a.ready = h->ready;
+    }
     CU(h, cudaEventRecord(h->ev0, h->stream));
     rc = do_optimize(h, a);
     if (rc) return rc;
@@ -507,7 +609,7 @@ int mincob_optimize_device(mincob_handle h, double *x, double *f, int32_t *statu
 
 int mincob_optimize(mincob_handle h, double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals,
                     double *coeffs, double *T) {
-    int rc = have_problems(h);
+    int rc = have_problems(h, true);
     if (rc) return rc;
     if (!x) return fail(h, MINCOB_E_INVALID, "x must be non-null");
     ON_DEVICE(h);
@@ -517,7 +619,8 @@ int mincob_optimize(mincob_handle h, double *x, double *f, int32_t *status, int3
         (rc = ensure(h, h->b_iters, ni)) || (rc = ensure(h, h->b_evals, ni)) || (rc = ensure(h, h->b_coeffs, nc)) ||
         (rc = ensure(h, h->b_T, nt)))
         return rc;
-    CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
+    if (h->upload_pending) { if ((rc = start_upload(h, x, (double *)h->b_x.p, nx))) return rc; }
+    else CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
     rc = mincob_optimize_device(h, (double *)h->b_x.p, (double *)h->b_f.p, (int32_t *)h->b_status.p,
                                 (int32_t *)h->b_iters.p, (int32_t *)h->b_evals.p, coeffs ? (double *)h->b_coeffs.p : nullptr,
                                 T ? (double *)h->b_T.p : nullptr);
@@ -775,7 +878,7 @@ static int optimize_sharded(mincob_ctx *h, bool gather_to_host, double *x, doubl
                             int32_t *evals, double *coeffs, double *T) {
     if (!h) return MINCOB_E_INVALID;
     if (!h->comm || h->nranks == 1) return mincob_optimize(h, x, f, status, iters, evals, coeffs, T);
-    int rc = have_problems(h);
+    int rc = have_problems(h, true);
     if (rc) return rc;
     if (!x || (gather_to_host && !coeffs)) return fail(h, MINCOB_E_INVALID, "x and coeffs_all must be non-null");
     ON_DEVICE(h);
@@ -785,7 +888,8 @@ static int optimize_sharded(mincob_ctx *h, bool gather_to_host, double *x, doubl
         (rc = ensure(h, h->b_iters, ni)) || (rc = ensure(h, h->b_evals, ni)) || (rc = ensure(h, h->b_coeffs, nc)) ||
         (rc = ensure(h, h->b_T, nt)) || (rc = ensure(h, h->b_gather, nc * h->nranks)))
         return rc;
-    CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
+    if (h->upload_pending) { if ((rc = start_upload(h, x, (double *)h->b_x.p, nx))) return rc; }
+    else CU(h, cudaMemcpyAsync(h->b_x.p, x, nx, cudaMemcpyHostToDevice, h->stream));
     // every rank must reach the collective, also when the parameter check short-circuits
     CU(h, cudaMemsetAsync(h->b_coeffs.p, 0, nc, h->stream));
     rc = mincob_optimize_device(h, (double *)h->b_x.p, (double *)h->b_f.p, (int32_t *)h->b_status.p,

@@ -507,7 +507,7 @@ def main():
 
         def e2e_step():
             h_x[...] = h_x0
-            mb.set_problems(hpb)                                       # H2D: head, tail, hpolys, hrows
+            mb.set_problems_async(hpb)                                 # H2D: head, tail, hpolys, hrows, chunked, overlapped by the kernel
             # H2D x; optimize; all-gather on the device; D2H of this rank's results into the shared result array
             mb.optimize_sharded_local_host_buffers(h_x, h_f, h_status, h_iters, h_evals, h_call, h_T)
         for _ in range(2):
@@ -529,7 +529,7 @@ def main():
         d2h = B * n * 8 + B * 8 + 3 * B * 4 + cnt * 8 + B * N * 8
         e2e = {"value": world * B * a.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / a.steps,
-               "api": "mincob_set_problems + mincob_optimize_sharded_local (host pointers, pinned)" +
+               "api": "mincob_set_problems_async + mincob_optimize_sharded_local (host pointers, pinned; the kernel starts while the batch is still uploading)" +
                       ("; bytes are per rank; every rank copies its own block of the result into one shared, page-locked host "
                        "array owned by rank 0 (the consumer), after the device-side all-gather" if world > 1 else ""),
                "ok_fraction": float((h_status >= 0).mean()), "result_complete_on_consumer": e2e_ok}

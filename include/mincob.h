@@ -126,6 +126,13 @@ int mincob_set_problems(mincob_handle h, int B, int N, int K, const double *head
                         const double *hpolys, const int32_t *hrows);
 int mincob_set_problems_device(mincob_handle h, int B, int N, int K, const double *head_d,
                                const double *tail_d, const double *hpolys_d, const int32_t *hrows_d);
+/*      Overlapped form of mincob_set_problems for large batches: returns at once; the arrays are uploaded in problem
+ *      order, in chunks, on a second stream, and the next mincob_optimize* call starts immediately -- its work queue
+ *      waits per problem for a device-side arrival counter, so all but the first chunk of the upload is hidden behind
+ *      the kernel.  The host arrays must be page-locked (mincob_host_alloc / mincob_host_register) and must not be
+ *      modified until that optimize call has returned.  Any other entry point waits for the complete upload. */
+int mincob_set_problems_async(mincob_handle h, int B, int N, int K, const double *head, const double *tail,
+                              const double *hpolys, const int32_t *hrows);
 
 /* ---- costFunctional (upstream gcopter.hpp) for every problem:
  *      the lbfgs_evaluate_t callback body (gcopter/lbfgs.hpp:200-202) as ONE kernel launch. */

@@ -184,6 +184,11 @@ public:
     void setProblems(int B, int N, int K, const double *head, const double *tail, const double *hpolys, const int32_t *hrows) {
         check(h, mincob_set_problems(h, B, N, K, head, tail, hpolys, hrows), "setProblems");
     }
+    // overlapped upload for large batches: page-locked arrays (mincob_host_alloc / mincob_host_register) that stay untouched
+    // until the following optimize() has returned; the kernel starts while the batch is still arriving
+    void setProblemsAsync(int B, int N, int K, const double *head, const double *tail, const double *hpolys, const int32_t *hrows) {
+        check(h, mincob_set_problems_async(h, B, N, K, head, tail, hpolys, hrows), "setProblemsAsync");
+    }
     void evaluate(const double *x, double *f, double *g) { check(h, mincob_evaluate(h, x, f, g), "evaluate"); }
     void optimize(double *x, double *f, int32_t *status, int32_t *iters, int32_t *evals, double *coeffs, double *T) {
         check(h, mincob_optimize(h, x, f, status, iters, evals, coeffs, T), "optimize");

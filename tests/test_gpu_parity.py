@@ -871,3 +871,38 @@ def test_division_free_decisions_match_reference_forms():
         mb.close()
     rel = np.abs(out[0]["f"] - out[1]["f"]) / np.abs(out[1]["f"])
     assert np.median(rel) <= 2e-3 and abs(out[0]["evals"].mean() / out[1]["evals"].mean() - 1.0) <= 0.05
+
+
+def test_overlapped_upload_gives_the_same_results(handles):
+    """mincob_set_problems_async: the batch is uploaded in chunks while the optimize kernel already runs (its work
+    queue waits per problem for the arrival counter).  Results are bit-identical to the synchronous upload, also
+    when the batch is replaced by another one right away (the second upload must wait for the first kernel), and any
+    other entry point called after an asynchronous upload sees the complete batch."""
+    mb = handles[3]
+    mb.set_params(default_params(3, max_iterations=40))
+    B = 20000                                                     # several chunks of 4096
+    pbs = [synth.make_problems(B, N=8, K=16, S=3, first=f) for f in (0, 50000)]
+    want = []
+    for pb in pbs:
+        mb.set_problems(pb)
+        want.append(mb.optimize(pb.x0()))
+    pin = api.pinned_empty
+
+    def pinned(pb):
+        q = synth.ProblemBatch(pb.S, pb.N, pb.K, pin(pb.head.shape), pin(pb.tail.shape), pin(pb.hpolys.shape),
+                               pin(pb.hrows.shape, np.int32), pb.q0, pb.T0)
+        q.head[...] = pb.head; q.tail[...] = pb.tail; q.hpolys[...] = pb.hpolys; q.hrows[...] = pb.hrows
+        return q
+    pp = [pinned(pb) for pb in pbs]
+    for rep in range(2):
+        for pb, ref in zip(pp, want):
+            mb.set_problems_async(pb)
+            got = mb.optimize(pb.x0())
+            for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+                np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    mb.set_problems_async(pp[0])
+    f, g = mb.evaluate(pp[0].x0())                                 # waits for the whole upload
+    mb.set_problems(pbs[0])
+    f2, g2 = mb.evaluate(pbs[0].x0())
+    np.testing.assert_array_equal(f, f2); np.testing.assert_array_equal(g, g2)
+    mb.set_params(default_params(3))
