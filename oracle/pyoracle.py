@@ -140,6 +140,28 @@ class Oracle:
         return dict(x=x, f=f, status=status, iters=iters, evals=evals, coeffs=coeffs, T=T,
                     driver="oracle/_ref (reference gcopter/lbfgs.hpp, verbatim)")
 
+    def ref_qp_build(self, iniPVA, finPVA, polys, times32, order=3, res=20, vel_box=4.0, acc_box=6.0):
+        """The matrices the reference's own QPSolver::solve (planner/qp_solver.hpp, compiled verbatim into
+        oracle/_ref/libref_qp.so) hands to OSQP: dict(hessian [n][n], constraints [m][n], lower [m], upper [m]), or None
+        when that library was not built (no reference tree).  iniPVA / finPVA 3x3 (rows axis, columns P,V,A);
+        polys [seg][rows][4] rows [n, b]; times32 float32 [seg]."""
+        so = os.path.join(_HERE, "_ref", "libref_qp.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        polys = _f64(polys); seg, rows = polys.shape[0], polys.shape[1]
+        ini, fin = _f64(iniPVA), _f64(finPVA)
+        t32 = np.ascontiguousarray(times32, dtype=np.float32)
+        d = 2 * order
+        n = seg * 3 * d
+        m = (6 + order * (seg - 1)) * 3 + res * (rows * seg) + res * 12 * seg
+        H = np.zeros((n, n)); A = np.zeros((m, n)); lo = np.zeros(m); up = np.zeros(m)
+        nn, mm = C.c_int(0), C.c_int(0)
+        rc = L.ref_qp_build(seg, rows, order, res, C.c_double(vel_box), C.c_double(acc_box), _ptr(ini), _ptr(fin), _ptr(polys),
+                            t32.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nn), C.byref(mm), _ptr(H), _ptr(A), _ptr(lo), _ptr(up))
+        assert rc == 0 and nn.value == n and mm.value == m, (rc, nn.value, n, mm.value, m)
+        return dict(hessian=H, constraints=A, lower=lo, upper=up, n_eq=(6 + order * (seg - 1)) * 3)
+
     def hardware_threads(self):
         return int(self.lib.orc_hardware_threads())
 

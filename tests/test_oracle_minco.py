@@ -196,6 +196,58 @@ def test_reference_qp_sensitivities_pin_energy_partials_and_propagate_grad(oracl
     np.testing.assert_allclose(gq, gq_ref, rtol=0, atol=2e-9 * np.abs(gq_ref).max())
 
 
+def _cpp_qp(oracle, c):
+    st, hp = c["state"], c["hpolys"]
+    ini = st[:, 0].reshape(3, 3); fin = st[:, 1].reshape(3, 3)            # rows axis, columns P,V,A
+    return oracle.ref_qp_build(ini, fin, hp.transpose(2, 0, 1), c["times"].astype(np.float32), order=3, res=int(c["res"]))
+
+
+@pytest.mark.parametrize("name", REF_QP_CASES)
+def test_reference_cpp_qp_solver_builds_the_matrices_of_its_python_twin(oracle, name):
+    """planner/qp_solver.hpp, compiled VERBATIM (oracle/_ref/libref_qp.so: ROS / OsqpEigen / Eigen stand-ins that record what
+    QPSolver::solve hands to OSQP), builds the same Q, A, b, G, h as the reference's Python twin did for the fixtures --
+    up to the float32 arithmetic the C++ uses for the powers of the durations (qp_solver.hpp:183-184,252; SURVEY Appendix C
+    quirk Q2): the fixtures that pin MINCO are the C++ back-end's own problem."""
+    c = load_ref_qp(name)
+    q = _cpp_qp(oracle, c)
+    if q is None:
+        pytest.skip("oracle/_ref/libref_qp.so not built (no reference tree on this box)")
+    meq, K, N, res = q["n_eq"], c["hpolys"].shape[0], len(c["times"]), int(c["res"])
+    f32 = 3e-7
+    np.testing.assert_allclose(q["hessian"], c["Q"], rtol=0, atol=f32 * np.abs(c["Q"]).max())
+    np.testing.assert_allclose(q["constraints"][:meq], c["A"], rtol=0, atol=f32 * np.abs(c["A"]).max())
+    np.testing.assert_array_equal(q["upper"][:meq], c["b"]); np.testing.assert_array_equal(q["lower"][:meq], c["b"])
+    rows, hs = [], []
+    for i in range(N):                        # the C++ interleaves corridor and box rows per sample, the twin keeps two arrays
+        for j in range(res):
+            s0 = i * res + j
+            rows += [c["G1"][s0 * K:(s0 + 1) * K], c["G2"][s0 * 12:(s0 + 1) * 12]]
+            hs += [c["h1"][s0 * K:(s0 + 1) * K], c["h2"][s0 * 12:(s0 + 1) * 12]]
+    G, h = np.vstack(rows), np.concatenate(hs)
+    np.testing.assert_allclose(q["constraints"][meq:], G, rtol=0, atol=f32 * np.abs(G).max())
+    np.testing.assert_array_equal(q["upper"][meq:], h)
+    assert np.isneginf(q["lower"][meq:]).all()
+
+
+@pytest.mark.parametrize("name", REF_QP_CASES)
+def test_reference_cpp_qp_matrices_reproduce_minco(oracle, name):
+    """Same KKT statement as test_reference_qp_matrices_reproduce_minco, with the matrices of the C++ back-end itself and
+    its float32 durations: the minimiser is the oracle's MINCO_S3NU at T = float32(times), to what float32 time powers in
+    Q and A allow."""
+    c = load_ref_qp(name)
+    q = _cpp_qp(oracle, c)
+    if q is None:
+        pytest.skip("oracle/_ref/libref_qp.so not built (no reference tree on this box)")
+    head, tail, wp, _ = ref_qp_problem(c, 5)
+    T = c["times"].astype(np.float32).astype(np.float64)
+    c2 = dict(c); c2["Q"] = q["hessian"]; c2["A"] = q["constraints"][:q["n_eq"]]; c2["b"] = q["upper"][:q["n_eq"]]
+    z, _, _ = ref_qp_kkt(c2, wp)
+    out = oracle.minco_forward(3, head, tail, wp, T)
+    zo = out["flat"].reshape(-1)
+    np.testing.assert_allclose(zo, z, rtol=0, atol=2e-5 * np.abs(z).max())
+    assert 0.5 * zo @ q["hessian"] @ zo == pytest.approx(out["energy"] / 2.0, rel=2e-5)     # float32 entries of Q
+
+
 @pytest.mark.parametrize("name", REF_QP_CASES)
 def test_reference_qp_inequality_rows_pin_sampling_layout(oracle, name):
     """G1 z - h1 (corridor) and G2 z - h2 (+-v, +-a boxes) of the reference, evaluated on the oracle's
