@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the parity / gather checks (they run outside the timed region)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the two-batches-in-flight measurement (`pipelined`)")
     a = ap.parse_args()
     preset = CONFIGS[a.config]
     a.batch = a.batch if a.batch is not None else preset["batch"]
@@ -450,6 +451,48 @@ def main():
                 "note": "windows whose net answer the planner would reject (a duration < 1e-10 on a used segment, i.e. the stop "
                         "token fired early: learning_planner.hpp:181-189) keep the trapezoid rule"}
 
+    # ---- two batches in flight (single rank): a second handle on a second stream works on the next batch while the first
+    #      one is in its launch tail.  Not the headline (`value` times strictly sequential steps); it shows what the
+    #      device sustains when batches stream in, which is what the tail costs per batch. ---------------------------------
+    pipelined = None
+    if world == 1 and not a.no_pipeline and net is None:
+        from allocnet_b200 import api as _api
+        s2 = torch.cuda.Stream(dev)
+        mb2 = _api.MincoBatch(prm, device=local)
+        mb2.set_stream(s2.cuda_stream)
+        mb2.set_problems_device(B, N, K, d_head, d_tail, d_hp, d_hr)
+        bufs = []
+        for _ in range(2):
+            bufs.append(dict(x=torch.empty_like(d_x0), f=torch.empty_like(d_f), st=torch.empty_like(d_status), it=torch.empty_like(d_iters),
+                             ev=torch.empty_like(d_evals), co=torch.empty(cnt, dtype=torch.float64, device=dev), T=torch.empty_like(d_T)))
+        lanes = ((mb, stream, bufs[0]), (mb2, s2, bufs[1]))
+
+        def pstep(k):
+            h, st_, b = lanes[k % 2]
+            with torch.cuda.stream(st_):
+                b["x"].copy_(d_x0)
+                h.optimize_device(b["x"], b["f"], b["st"], b["it"], b["ev"], b["co"], b["T"])
+        for k in range(4):
+            pstep(k)
+        torch.cuda.synchronize(dev)
+        nst = max(2 * a.steps, 6)
+        p0, p1, pj = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event()
+        p0.record(stream)
+        s2.wait_event(p0)
+        for k in range(nst):
+            pstep(k)
+        pj.record(s2)
+        stream.wait_event(pj)
+        p1.record(stream)
+        torch.cuda.synchronize(dev)
+        pms = p0.elapsed_time(p1)
+        same = bool(torch.equal(bufs[0]["x"], d_x) and torch.equal(bufs[1]["x"], d_x)) if not a.no_check else None
+        pipelined = {"value": B * nst / (pms * 1e-3), "unit": UNIT, "steps": nst, "ms_per_step": pms / nst, "batches_in_flight": 2,
+                     "results_identical_to_sequential": same,
+                     "note": "two handles on two streams, alternating batches: the next batch's blocks become resident as the previous "
+                             "batch's blocks retire, so its launch tail is filled; latency of one batch is unchanged"}
+        mb2.close()
+
     # ---- the per-evaluation kernel on its own (the lbfgs_evaluate_t body for the whole batch, one launch): this is the
     #      launch BASELINE.json's "one fused kernel per L-BFGS evaluation" describes, with its algorithmic HBM bytes -------
     evk = None
@@ -616,6 +659,8 @@ def main():
         if evk is not None:
             evk["frac_of_hbm_peak"] = evk["achieved_gbs"] / peak
             line["evaluate_kernel"] = evk
+        if pipelined is not None:
+            line["pipelined"] = pipelined
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not a.no_cpu:
