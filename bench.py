@@ -190,13 +190,16 @@ def run_reference(a):
 
 
 def sass_fingerprint():
-    """Identity of the built optimize kernel: size and mtime-independent hash of allocnet_b200/libmincob.so; the fp64 flop
-    count per evaluation in profiles/optimize_kernel_traffic.json is only valid for the build it was captured from."""
+    """Identity of the kernel the library was built from: sha256 over the CUDA sources (allocnet_b200/csrc).  The fp64 flop
+    count per evaluation in profiles/optimize_kernel_traffic.json is only valid for the kernel it was captured from."""
     import hashlib
-    from allocnet_b200 import api
+    d = os.path.join(ROOT, "allocnet_b200", "csrc")
+    h = hashlib.sha256()
     try:
-        with open(api.LIB_PATH, "rb") as fh:
-            return hashlib.sha256(fh.read()).hexdigest()[:16]
+        for name in sorted(os.listdir(d)):
+            with open(os.path.join(d, name), "rb") as fh:
+                h.update(name.encode()); h.update(fh.read())
+        return h.hexdigest()[:16]
     except OSError:
         return None
 
@@ -603,7 +606,7 @@ def main():
                 tj = json.load(fh)
             if tj.get("batch") == B and tj.get("pieces") == N and tj.get("K") == K and tj.get("S", 3) == S:
                 traffic = tj.get("dram_bytes_per_launch")
-                stale = tj.get("library_sha256_16") not in (None, sass_fingerprint())
+                stale = tj.get("kernel_source_sha256_16") not in (None, sass_fingerprint())
                 if tj.get("fp64_flops_per_eval") and not stale:
                     # what actually bounds the kernel: executed fp64 flops (2 per DFMA, 1 per DADD/DMUL, predicated-on
                     # threads only; counted by ncu per evaluation for this configuration) over the live kernel time,
@@ -616,8 +619,8 @@ def main():
                             "flops_source": tj.get("source")}
                 elif stale:
                     traffic = None
-                    print("[bench] profiles/optimize_kernel_traffic.json was captured from another build of libmincob.so "
-                          "(library_sha256_16 differs): traffic / roofline_fp64 withheld; re-run tools/update_profiles.py",
+                    print("[bench] profiles/optimize_kernel_traffic.json was captured from another version of allocnet_b200/csrc "
+                          "(kernel_source_sha256_16 differs): traffic / roofline_fp64 withheld; re-run tools/update_profiles.py",
                           file=sys.stderr)
         except Exception as e:
             print(f"[bench] no traffic / fp64 record: {e}", file=sys.stderr)

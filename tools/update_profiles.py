@@ -35,11 +35,9 @@ flops = (2 * per("dfma") + per("dadd") + per("dmul")) * cyc
 bench = json.loads(open(os.path.join(G, "bench.json")).read().strip().split("\n")[-1])
 cfg = bench["config"]
 evals = bench["mean_evals_per_traj"] * cfg["batch_per_gpu"]
-import hashlib
 sys.path.insert(0, ROOT)
-from allocnet_b200 import api
-lib_hash = hashlib.sha256(open(api.LIB_PATH, "rb").read()).hexdigest()[:16]
-out = {"library_sha256_16": lib_hash, "kernel": d["Kernel Name"], "batch": cfg["batch_per_gpu"], "pieces": cfg["pieces"], "K": cfg["K"], "S": cfg["S"],
+import bench as _bench
+out = {"kernel_source_sha256_16": _bench.sass_fingerprint(), "kernel": d["Kernel Name"], "batch": cfg["batch_per_gpu"], "pieces": cfg["pieces"], "K": cfg["K"], "S": cfg["S"],
        "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr),
        "fp64_flops_per_launch": flops, "fp64_flops_per_eval": flops / evals,
        "fp64_note": "thread-level, predicated-on: (2*dfma + dadd + dmul) inst/cycle x elapsed cycles = "
