@@ -4,6 +4,8 @@
 // objects compile in parallel.
 // ============================================================================
 #include "../../include/mincob.h"
+#include <cstdlib>
+
 #include "launch.h"
 #include "lbfgs_device.cuh"
 
@@ -244,7 +246,7 @@ LaunchResult launch_evaluate(cudaStream_t st, int sm_count, const DevParams &dp,
 // Shared memory per block and grid of the persistent optimize kernel.  Half-planes are staged in
 // shared memory when at least MINCOB_MINB blocks per SM still fit; otherwise they are read from global.
 struct OptPlan {
-    int psmem, rep, blocks;
+    int psmem, rep, blocks;   // psmem: 0 rows read from global memory, 1 staged in shared memory
     size_t smem, hist_bytes, mult_bytes, park_bytes;
     int code;
     cudaError_t err;
@@ -255,14 +257,20 @@ struct OptPlan {
 #endif
 constexpr int FASTMEM = MINCOB_FASTMEM;   // 0: every depth takes the rolled loops (experiments)
 using OptKernel = void (*)(const DevParams, const BatchArgs);
-template <bool PSMEM, int MEM>
+template <int PSM, int MEM, bool FRZ>
 static OptKernel opt_kernel(bool rep) {
-    if (rep) return optimize_kernel<S, LPT, THREADS, PSMEM, MEM, true>;
-    return optimize_kernel<S, LPT, THREADS, PSMEM, MEM, false>;
+    if (rep) return optimize_kernel<S, LPT, THREADS, PSM, MEM, true, FRZ>;
+    return optimize_kernel<S, LPT, THREADS, PSM, MEM, false, FRZ>;
 }
-static OptKernel pick_kernel(bool psmem, int mem, bool rep) {
-    if (mem == FASTMEM) return psmem ? opt_kernel<true, FASTMEM>(rep) : opt_kernel<false, FASTMEM>(rep);
-    return psmem ? opt_kernel<true, 0>(rep) : opt_kernel<false, 0>(rep);
+template <int MEM, bool FRZ>
+static OptKernel opt_kernel_m(int psm, bool rep) {
+    return psm == 1 ? opt_kernel<1, MEM, FRZ>(rep) : opt_kernel<0, MEM, FRZ>(rep);
+}
+// frz: the fixed-time specialisation exists for the default history depth; other depths run the generic kernel, which
+// honours DevParams::freeze at run time (same bits)
+static OptKernel pick_kernel(int psm, int mem, bool rep, bool frz) {
+    if (mem == FASTMEM) return (frz && FASTMEM > 0) ? opt_kernel_m<FASTMEM, true>(psm, rep) : opt_kernel_m<FASTMEM, false>(psm, rep);
+    return opt_kernel_m<0, false>(psm, rep);
 }
 static int blocks_per_sm(OptKernel kern, size_t smem, cudaError_t &e) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -279,15 +287,19 @@ static size_t smem_bytes(int N, int K, const DevParams &dp, int psmem) {
     return ((size_t)GPB * optimize_group_doubles(S, N, K, dp.mem, dp.past, psmem, LPT) +
             (size_t)(SPB - GPB) * optimize_small_doubles(S, dp.mem, dp.past, LPT)) * sizeof(double);
 }
+// MINCOB_NO_FRZ in the environment sends the fixed-time mode through the generic kernel (DevParams::freeze at run time):
+// the parity suite compares the two, they must agree bit for bit.
+static bool use_frz(const DevParams &dp) { return dp.freeze != 0 && getenv("MINCOB_NO_FRZ") == nullptr; }
 static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs &a) {
     OptPlan pl{0, 0, 0, 0, 0, 0, 0, 0, cudaSuccess};
+    const bool frz = use_frz(dp);
     const bool have = a.hpolys && a.hrows && a.K > 0;
     const bool can_rep = Lanes<LPT>::GPW > 1;
     int per_sm = 0;
     // occupancy does not depend on REP (same registers cap, same shared memory): plan with the throughput kernel
     if (have && dp.penalties) {
         pl.smem = smem_bytes(a.N, a.K, dp, 1);
-        per_sm = blocks_per_sm(pick_kernel(true, dp.mem, false), pl.smem, pl.err);
+        per_sm = blocks_per_sm(pick_kernel(1, dp.mem, false, frz), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
         pl.psmem = per_sm >= MINCOB_MINB || per_sm * WARPS >= 8;   // staging must leave at least 8 warps per SM resident
 #ifdef MINCOB_GLOBAL_PLANES   // experiment: never stage half-planes in shared memory (occupancy then depends on registers only)
@@ -296,14 +308,14 @@ static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs 
     }
     if (!pl.psmem) {
         pl.smem = smem_bytes(a.N, a.K, dp, 0);
-        per_sm = blocks_per_sm(pick_kernel(false, dp.mem, false), pl.smem, pl.err);
+        per_sm = blocks_per_sm(pick_kernel(false, dp.mem, false, frz), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
     }
     if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
     pl.blocks = per_sm * sm_count;
     pl.rep = can_rep && (dp.mapping == MINCOB_MAP_LATENCY || (dp.mapping == MINCOB_MAP_AUTO && a.B <= pl.blocks * WARPS));
     if (pl.rep) {
-        per_sm = blocks_per_sm(pick_kernel(pl.psmem, dp.mem, true), pl.smem, pl.err);
+        per_sm = blocks_per_sm(pick_kernel(pl.psmem, dp.mem, true, frz), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;
         if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
         pl.blocks = per_sm * sm_count;
@@ -338,7 +350,8 @@ LaunchResult launch_optimize(cudaStream_t st, int sm_count, const DevParams &dp,
     BatchArgs b = a;
     b.mult = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes);
     b.lpark = reinterpret_cast<double *>(reinterpret_cast<char *>(a.hist) + pl.hist_bytes + pl.mult_bytes);
-    pick_kernel(pl.psmem, dp.mem, pl.rep)<<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
+    const bool frz = use_frz(dp);
+    pick_kernel(pl.psmem, dp.mem, pl.rep, frz)<<<pl.blocks, THREADS, pl.smem, st>>>(dp, b);
     LaunchResult r = ok(cudaGetLastError());
     r.mapping = pl.rep ? MINCOB_MAP_LATENCY : MINCOB_MAP_THROUGHPUT;
     return r;

@@ -145,11 +145,17 @@ __host__ __device__ inline int optimize_group_doubles(int S, int N, int K, int m
 // recursion is unrolled over registers, the first MINCOB_HDEP history pairs are requested right after the
 // evaluation (their L2 latency is covered by the reductions and the scalar decisions) and the others
 // MINCOB_HDEP steps ahead of their use.  MEM == 0: any depth, rolled loops with two slots in flight.
+// PSM: 0 half-planes read from global memory, 1 staged in shared memory.
 // REP: latency mapping, "one warp per trajectory" (BASELINE.json north_star): the GPW groups of a warp fetch the SAME
 // problem and run the same state machine on bitwise identical state; only the penalty samples are split among them
 // (cost_functional<.., REP>).  Used when the batch is too small to fill the device with one group per problem.
-template <int S, int LPT, int THREADS, bool PSMEM, int MEM, bool REP>
+// FRZ: fixed-time mode (MINCOB_FLAG_FREEZE_TIMES, the call the reference makes: learning_planner.hpp:196) as its own
+// instantiation: the block factorisation of a problem is computed by its first evaluation and reused by all later ones,
+// and no time gradient is formed.  Bit-identical to the generic kernel run with P.freeze
+// (tests/test_gpu_parity.py::test_fixed_time_kernel_equals_generic_kernel).
+template <int S, int LPT, int THREADS, int PSM, int MEM, bool REP, bool FRZ = false>
 __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const DevParams P, const BatchArgs a) {
+    constexpr bool PSMEM = PSM != 0;
     constexpr unsigned FULL = 0xffffffffu;
     using LN = Lanes<LPT>;
     constexpr int SPB = (THREADS / 32) * LN::SPW;   // group slots per block (real groups + dummy groups)
@@ -291,9 +297,13 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
 #pragma unroll
             for (int i = 0; i < 4; ++i) { xp[i] = lstore.get(i); gp[i] = lstore.get(4 + i); d[i] = park_dir[i * LPT]; }
         };
-        const double f = cost_functional<S, LPT, PSMEM, GlobalStore, REP>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, unpark);
+        // fixed-time kernel: a newly fetched problem anywhere in the warp makes the whole warp factorise (the other
+        // groups recompute and store the multipliers they already hold)
+        const bool refac = !FRZ || __any_sync(FULL, phase == PH_FIRST);
+        const double f = cost_functional<S, LPT, PSM, GlobalStore, REP, decltype(unpark), FRZ>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, unpark, refac);
 #else
-        const double f = cost_functional<S, LPT, PSMEM, GlobalStore, REP>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq);
+        const bool refac = !FRZ || __any_sync(FULL, phase == PH_FIRST);
+        const double f = cost_functional<S, LPT, PSM, GlobalStore, REP, NoHook, FRZ>(P, FULL, lig, phase == PH_IDLE ? 0 : N, rounds, pv, mstore, x[0], xq, g[0], gq, NoHook(), refac);
 #endif
         g[1] = gq[0]; g[2] = gq[1]; g[3] = gq[2];
 #if MINCOB_PARK

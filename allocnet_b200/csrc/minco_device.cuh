@@ -295,11 +295,15 @@ __device__ __forceinline__ void sweep_apply(unsigned mask, int rounds, const dou
 // Output: sp (coefficients + factorisation), chat (normalised coefficients c_k T^k).
 // `rounds` = (pieces of the launch) - 2, the same for every group of the warp (a group that is idle
 // passes N = 0 and carries identity rows through the same rounds).
-template <int S, int LPT, class ST>
+// FRZ (fixed-time mode, MINCOB_FLAG_FREEZE_TIMES): the block factorisation depends on the durations only, which are
+// data in that mode.  `refac` (warp-uniform) = factorise and store the multipliers (the first evaluation of a problem);
+// otherwise the stored multipliers are loaded and only the right-hand sides are swept (sweep_apply), which performs the
+// same operations on the same values: the two paths give identical bits.
+template <int S, int LPT, class ST, bool FRZ = false>
 __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int rounds, double Tin, const double (&P0)[3],
                                              const double (&P1)[3], const double (&hd)[S - 1][3],
                                              const double (&td)[S - 1][3], Spline<S, LPT, ST> &sp,
-                                             double (&chat)[2 * S][3]) {
+                                             double (&chat)[2 * S][3], bool refac = true) {
     constexpr int D = 2 * S, b = S - 1;
     using SP = Spline<S, LPT, ST>;
     using HK = HermiteK<S>;
@@ -319,16 +323,12 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
     for (int x = 0; x < 3; ++x) dP[x] = active ? P1[x] - P0[x] : 0.0;
 
     // blocks of W(T) = t5 * lam_a lam_c What[a][c]; start unknown rows 1..S-1, end rows S+1..2S-1
-    double A[b][b], Bm[b][b], C[b][b], wa[b], wb[b];
+    double Bm[b][b], wa[b], wb[b];
 #pragma unroll
     for (int a = 0; a < b; ++a) {
         const double la = t5 * lam[a + 1];
 #pragma unroll
-        for (int c = 0; c < b; ++c) {
-            A[a][c] = la * lam[c + 1] * HK::W(1 + a, 1 + c);
-            Bm[a][c] = la * lam[c + 1] * HK::W(1 + a, S + 1 + c);
-            C[a][c] = la * lam[c + 1] * HK::W(S + 1 + a, S + 1 + c);
-        }
+        for (int c = 0; c < b; ++c) Bm[a][c] = la * lam[c + 1] * HK::W(1 + a, S + 1 + c);
         wa[a] = la * HK::W(1 + a, S);
         wb[a] = la * HK::W(S + 1 + a, S);
     }
@@ -347,120 +347,146 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
             }
             e[a][x] = ev; f[a][x] = fv;
         }
-    // block row of junction `lig` (between piece lig-1 and piece lig)
-    double Dm[b][b], U[b][b], L[b][b], r[b][3];
+    // right-hand side of junction `lig` (between piece lig-1 and piece lig)
+    double r[b][3];
     const bool junction = (lig >= 1) && (lig < N);
 #pragma unroll
-    for (int a = 0; a < b; ++a) {
-#pragma unroll
-        for (int c = 0; c < b; ++c) {
-            const double Cp = sh_up<LPT>(mask, C[a][c], 1);
-            const double Bp = sh_up<LPT>(mask, Bm[c][a], 1);  // transposed: L = B_{j-1}^T
-            Dm[a][c] = junction ? Cp + A[a][c] : (a == c ? 1.0 : 0.0);
-            U[a][c] = (junction && lig < N - 1) ? Bm[a][c] : 0.0;
-            L[a][c] = (junction && lig >= 2) ? Bp : 0.0;
-        }
+    for (int a = 0; a < b; ++a)
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
             const double ep = sh_up<LPT>(mask, e[a][x], 1);
             r[a][x] = junction ? -(ep + f[a][x]) : 0.0;
         }
-    }
-    // forward elimination.  M_j = L_j Dinv'_{j-1};  D'_j = D_j - M_j U_{j-1} with U_{j-1} = L_j^T (symmetry);
-    // r'_j = r_j - M_j r'_{j-1}.  Each round every lane redoes its row from its ORIGINAL D, r and its
-    // neighbour's current values: row j is final after round j-1 and is reproduced unchanged afterwards.
-    double Dinv[b][b], M[b][b], rr[b][3];
-    inv_small<b>(Dm, Dinv);
-#pragma unroll
-    for (int a = 0; a < b; ++a) {
-#pragma unroll
-        for (int c = 0; c < b; ++c) M[a][c] = 0.0;
-#pragma unroll
-        for (int x = 0; x < 3; ++x) rr[a][x] = r[a][x];
-    }
-#pragma unroll 1
-    for (int t = 0; t < rounds; ++t) {
-        double Dp[b][b], rp[b][3];
-#pragma unroll
-        for (int a = 0; a < b; ++a) {
-#pragma unroll
-            for (int c = 0; c < b; ++c) Dp[a][c] = sh_up<LPT>(mask, Dinv[a][c], 1);
-#pragma unroll
-            for (int x = 0; x < 3; ++x) rp[a][x] = sh_up<LPT>(mask, rr[a][x], 1);
-        }
-        double Dn[b][b];
-#pragma unroll
-        for (int a = 0; a < b; ++a) {
-#pragma unroll
-            for (int c = 0; c < b; ++c) {
-                double acc = 0.0;
-#pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(L[a][k], Dp[k][c], acc);
-                M[a][c] = acc;
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < b; ++a) {
-#pragma unroll
-            for (int c = 0; c < b; ++c) {
-                double acc = Dm[a][c];
-#pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(-M[a][k], L[c][k], acc);
-                Dn[a][c] = acc;
-            }
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double acc = r[a][x];
-#pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(-M[a][k], rp[k][x], acc);
-                rr[a][x] = acc;
-            }
-        }
-        inv_small<b>(Dn, Dinv);
-    }
-    // back substitution  y_j = Dinv'_j (r'_j - U_j y_{j+1}), same scheme from the far end
     double y[b][3];
+    if (!FRZ || refac) {
+        double A[b][b], C[b][b];
 #pragma unroll
-    for (int a = 0; a < b; ++a) {
+        for (int a = 0; a < b; ++a) {
+            const double la = t5 * lam[a + 1];
 #pragma unroll
-        for (int k = 0; k < b; ++k) {
-            sp.st.put(SP::im(a, k), M[a][k]);
-            sp.st.put(SP::idi(a, k), Dinv[a][k]);
-            sp.st.put(SP::iu(a, k), U[a][k]);
+            for (int c = 0; c < b; ++c) {
+                A[a][c] = la * lam[c + 1] * HK::W(1 + a, 1 + c);
+                C[a][c] = la * lam[c + 1] * HK::W(S + 1 + a, S + 1 + c);
+            }
         }
+        // block row of junction `lig`
+        double Dm[b][b], U[b][b], L[b][b];
 #pragma unroll
-        for (int x = 0; x < 3; ++x) {
-            double acc = 0.0;
+        for (int a = 0; a < b; ++a) {
 #pragma unroll
-            for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], rr[k][x], acc);
-            y[a][x] = acc;
+            for (int c = 0; c < b; ++c) {
+                const double Cp = sh_up<LPT>(mask, C[a][c], 1);
+                const double Bp = sh_up<LPT>(mask, Bm[c][a], 1);  // transposed: L = B_{j-1}^T
+                Dm[a][c] = junction ? Cp + A[a][c] : (a == c ? 1.0 : 0.0);
+                U[a][c] = (junction && lig < N - 1) ? Bm[a][c] : 0.0;
+                L[a][c] = (junction && lig >= 2) ? Bp : 0.0;
+            }
         }
-    }
+        // forward elimination.  M_j = L_j Dinv'_{j-1};  D'_j = D_j - M_j U_{j-1} with U_{j-1} = L_j^T (symmetry);
+        // r'_j = r_j - M_j r'_{j-1}.  Each round every lane redoes its row from its ORIGINAL D, r and its
+        // neighbour's current values: row j is final after round j-1 and is reproduced unchanged afterwards.
+        double Dinv[b][b], M[b][b], rr[b][3];
+        inv_small<b>(Dm, Dinv);
+#pragma unroll
+        for (int a = 0; a < b; ++a) {
+#pragma unroll
+            for (int c = 0; c < b; ++c) M[a][c] = 0.0;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) rr[a][x] = r[a][x];
+        }
 #pragma unroll 1
-    for (int t = 0; t < rounds; ++t) {
-        double yn[b][3], w[b][3];
+        for (int t = 0; t < rounds; ++t) {
+            double Dp[b][b], rp[b][3];
 #pragma unroll
-        for (int a = 0; a < b; ++a)
+            for (int a = 0; a < b; ++a) {
 #pragma unroll
-            for (int x = 0; x < 3; ++x) yn[a][x] = sh_dn<LPT>(mask, y[a][x], 1);
+                for (int c = 0; c < b; ++c) Dp[a][c] = sh_up<LPT>(mask, Dinv[a][c], 1);
 #pragma unroll
-        for (int a = 0; a < b; ++a)
+                for (int x = 0; x < 3; ++x) rp[a][x] = sh_up<LPT>(mask, rr[a][x], 1);
+            }
+            double Dn[b][b];
 #pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double acc = rr[a][x];
+            for (int a = 0; a < b; ++a) {
 #pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(-U[a][k], yn[k][x], acc);
-                w[a][x] = acc;
+                for (int c = 0; c < b; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < b; ++k) acc = fma(L[a][k], Dp[k][c], acc);
+                    M[a][c] = acc;
+                }
             }
 #pragma unroll
-        for (int a = 0; a < b; ++a)
+            for (int a = 0; a < b; ++a) {
+#pragma unroll
+                for (int c = 0; c < b; ++c) {
+                    double acc = Dm[a][c];
+#pragma unroll
+                    for (int k = 0; k < b; ++k) acc = fma(-M[a][k], L[c][k], acc);
+                    Dn[a][c] = acc;
+                }
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    double acc = r[a][x];
+#pragma unroll
+                    for (int k = 0; k < b; ++k) acc = fma(-M[a][k], rp[k][x], acc);
+                    rr[a][x] = acc;
+                }
+            }
+            inv_small<b>(Dn, Dinv);
+        }
+        // back substitution  y_j = Dinv'_j (r'_j - U_j y_{j+1}), same scheme from the far end
+#pragma unroll
+        for (int a = 0; a < b; ++a) {
+#pragma unroll
+            for (int k = 0; k < b; ++k) {
+                sp.st.put(SP::im(a, k), M[a][k]);
+                sp.st.put(SP::idi(a, k), Dinv[a][k]);
+                sp.st.put(SP::iu(a, k), U[a][k]);
+            }
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], w[k][x], acc);
+                for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], rr[k][x], acc);
                 y[a][x] = acc;
             }
+        }
+#pragma unroll 1
+        for (int t = 0; t < rounds; ++t) {
+            double yn[b][3], w[b][3];
+#pragma unroll
+            for (int a = 0; a < b; ++a)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) yn[a][x] = sh_dn<LPT>(mask, y[a][x], 1);
+#pragma unroll
+            for (int a = 0; a < b; ++a)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    double acc = rr[a][x];
+#pragma unroll
+                    for (int k = 0; k < b; ++k) acc = fma(-U[a][k], yn[k][x], acc);
+                    w[a][x] = acc;
+                }
+#pragma unroll
+            for (int a = 0; a < b; ++a)
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < b; ++k) acc = fma(Dinv[a][k], w[k][x], acc);
+                    y[a][x] = acc;
+                }
+        }
+    } else {
+        // durations unchanged since the multipliers were stored: sweep the right-hand side only
+        double fac[SP::NM];
+#pragma unroll
+        for (int i = 0; i < SP::NM; ++i) fac[i] = sp.st.get(i);
+#pragma unroll
+        for (int a = 0; a < b; ++a)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) y[a][x] = r[a][x];
+        sweep_apply<S, LPT, ST>(mask, rounds, fac, y);
     }
     // boundary states of this piece, scaled: sh[d] = T^d * (d-th derivative); rows 0..S-1 start,
     // S..2S-1 end (row S holds dP = P1 - P0).  Not kept: spline_adjoint recomputes them from c.
@@ -500,7 +526,8 @@ __device__ __forceinline__ void spline_solve(unsigned mask, int lig, int N, int 
 
 // getEnergy + getEnergyPartialGradByCoeffs + getEnergyPartialGradByTimes for this piece
 // (SURVEY.md Appendix A.3 in normalised form: E_i = T^(1-2S) chat^T Qhat chat).
-template <int S, int LPT, class ST>
+// FRZ: the partial derivative by the duration is not wanted (fixed-time mode): gT = 0.
+template <int S, int LPT, class ST, bool FRZ = false>
 __device__ __forceinline__ void energy_partials(const Spline<S, LPT, ST> &sp, const double (&chat)[2 * S][3], bool active,
                                                 double &energy, double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S;
@@ -522,19 +549,21 @@ __device__ __forceinline__ void energy_partials(const Spline<S, LPT, ST> &sp, co
 #pragma unroll
             for (int c = S; c < D; ++c) {
                 qc += HK::Q(a, c) * chat[c][x];
-                qt += (HK::Q(a, c) * (a + c - 2 * S + 1)) * chat[c][x];
+                if (!FRZ) qt += (HK::Q(a, c) * (a + c - 2 * S + 1)) * chat[c][x];
             }
             e += chat[a][x] * qc;
-            et += chat[a][x] * qt;
+            if (!FRZ) et += chat[a][x] * qt;
             G[a][x] = 2.0 * sp.t5 * tp[a] * qc;   // lanes >= N hold zero coefficients (spline_solve): every term is 0 there
         }
     energy = sp.t5 * e;
-    gT = sp.t5 * sp.iT * et;
+    gT = FRZ ? 0.0 : sp.t5 * sp.iT * et;
 }
 
 // One half-plane row (nx,ny,nz,d); rows are 32-byte aligned.  PSMEM = true: the row sits in the
 // group's shared-memory stage (two LDS.128); false: 256-bit read-only global load.
 struct __align__(32) Plane { double x, y, z, w; };
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
 template <bool PSMEM>
 __device__ __forceinline__ Plane load_plane(const double *p) {
     Plane r;
@@ -557,7 +586,11 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
 // K > 32, e.g. the reference's polytopes padded to 50 rows, learning_planner.hpp:40,157-168); K <= MINCOB_MAX_ROWS = 64.
 // REP (latency mapping): this lane evaluates only the samples j = jbase + u * jstride; the caller adds the
 // replicas' partial sums.  REP = false: every sample, in order.
-template <int S, int LPT, bool PSMEM, bool REP, class ST>
+// PSM: where the rows are.  0: global memory (C-ABI layout); 1: the group's shared-memory stage.  (A hybrid -- the
+// first rows of polytopes too large to stage whole in the stage, the rest in global memory -- was built and measured in
+// round 2: no gain at any split, profiles/r02_tail_experiments.md section 7.)
+// FRZ (fixed-time mode): the time-gradient terms (through the sample times and the quadrature weights) are not computed.
+template <int S, int LPT, int PSM, bool REP, class ST, bool FRZ = false>
 __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT, ST> &sp, const double *planes,
                                               int rstride, int K, int jbase, int jstride, double &cost,
                                               double (&G)[2 * S][3], double &gT) {
@@ -592,22 +625,20 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             }
             // rows in shared memory: one per trip (code size); rows in global memory (K too large to stage): several
             // loads in flight per trip, the L2 latency is what that loop waits for
-            constexpr int UK = PSMEM ? MINCOB_UNROLL_K : MINCOB_UNROLL_KG;
-#pragma unroll 1
-            for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
-                unsigned pm = 0u;
-                const int k1 = min(K, k0 + 32);
+            auto scan = [&](auto in_smem, const double *base, int stride, int ka, int kb, unsigned &pm) {
+                constexpr bool SM = decltype(in_smem)::value;
+                constexpr int UK = SM ? MINCOB_UNROLL_K : MINCOB_UNROLL_KG;
 #if MINCOB_PLANE_PREFETCH
                 // software pipelining by one row: the next row's load is in flight while this row's tests issue
-                Plane hnext = load_plane<PSMEM>(planes + (size_t)(k0 < k1 ? k0 : 0) * rstride);
+                Plane hnext = load_plane<SM>(base + (size_t)(ka < kb ? ka : 0) * stride);
 #endif
 #pragma unroll UK
-                for (int k = k0; k < k1; ++k) {
+                for (int k = ka; k < kb; ++k) {
 #if MINCOB_PLANE_PREFETCH
                     const Plane h = hnext;
-                    hnext = load_plane<PSMEM>(planes + (size_t)(k + 1 < k1 ? k + 1 : k) * rstride);
+                    hnext = load_plane<SM>(base + (size_t)(k + 1 < kb ? k + 1 : k) * stride);
 #else
-                    const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+                    const Plane h = load_plane<SM>(base + (size_t)k * stride);
 #endif
                     int all = -1;
 #pragma unroll
@@ -618,6 +649,13 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                     }
                     pm |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
                 }
+            };
+#pragma unroll 1
+            for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
+                unsigned pm = 0u;
+                const int k1 = min(K, k0 + 32);
+                if constexpr (PSM == 1) scan(TrueT(), planes, rstride, k0, k1, pm);
+                else scan(FalseT(), planes, rstride, k0, k1, pm);
                 if (k0 == 0) pm0 = pm; else pm1 = pm;
             }
 #pragma unroll
@@ -671,7 +709,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                         while (todo != 0u) {
                             const int k = 32 * w + __ffs(todo) - 1;
                             todo &= todo - 1u;
-                            const Plane h = load_plane<PSMEM>(planes + (size_t)k * rstride);
+                            const Plane h = load_plane<PSM == 1>(planes + (size_t)k * rstride);
                             const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
                             if (v > 0.0) {
                                 smoothed_l1_pos(P.mu, imu, v, fv, df);
@@ -705,10 +743,12 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 double dsum = 0.0;
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
-                    double sn = 0.0;
+                    if (!FRZ) {
+                        double sn = 0.0;
 #pragma unroll
-                    for (int k = 4; k < D; ++k) sn = fma(cfall(k, 4) * pw[k - 4], sp.c[k][x], sn);
-                    dsum += gP[x] * vel[x] + gV[x] * acc[x] + gA[x] * jer[x] + gJ[x] * sn;
+                        for (int k = 4; k < D; ++k) sn = fma(cfall(k, 4) * pw[k - 4], sp.c[k][x], sn);
+                        dsum += gP[x] * vel[x] + gV[x] * acc[x] + gA[x] * jer[x] + gJ[x] * sn;
+                    }
                     const double wP = w * gP[x], wV = w * gV[x], wA = w * gA[x], wJ = w * gJ[x];
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
@@ -719,7 +759,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                         G[k][x] += t;
                     }
                 }
-                gT += dsum * (j * ikap) * w + node * pena * ikap;
+                if (!FRZ) gT += dsum * (j * ikap) * w + node * pena * ikap;
                 cost += w * pena;
             }
         }
@@ -728,7 +768,8 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
 
 // propogateGrad: G = dF/dc_i, gTp = partial dF/dT_i  ->  total dJ/dq_lig (junction lig, lanes
 // 1..N-1) and dJ/dT_lig (lanes 0..N-1).  See oracle/reduced_proto.py for the derivation.
-template <int S, int LPT, class ST>
+// FRZ (fixed-time mode): only dJ/dq is computed (gT = 0): the boundary states, What (L s) and the m^T W' s terms drop out.
+template <int S, int LPT, class ST, bool FRZ = false>
 __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, int rounds, const Spline<S, LPT, ST> &sp,
                                                const double (&G)[2 * S][3], double gTp, double (&gq)[3], double &gT) {
     constexpr int D = 2 * S, b = S - 1;
@@ -748,7 +789,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
             gh[k][x] = G[k][x] * ip;
-            kGc += (double)k * G[k][x] * sp.c[k][x];
+            if (!FRZ) kGc += (double)k * G[k][x] * sp.c[k][x];
         }
         ip *= sp.iT;
     }
@@ -769,7 +810,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
     // scaled boundary states of this piece from its coefficients (chat_k = c_k T^k):
     //   start sh[d] = d! chat_d,  end sh[S+d] = sum_k k!/(k-d)! chat_k,  sh[S] = dP = sum_{k>=1} chat_k
     double sh[D][3];
-    {
+    if (!FRZ) {
         double tk = 1.0;
         double chat[D][3];
 #pragma unroll
@@ -825,22 +866,25 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
         double wm[D], ws[D];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-            double vm = 0.0, vs = HK::W(a, S) * sh[S][x];
+            if (FRZ && a != 0 && a != S) continue;   // only rows 0 and S of What (L m) reach dJ/dq
+            double vm = 0.0, vs = FRZ ? 0.0 : HK::W(a, S) * sh[S][x];
 #pragma unroll
             for (int d = 1; d < S; ++d) {
                 vm = fma(HK::W(a, S + d), lm[S + d][x], fma(HK::W(a, d), lm[d][x], vm));
-                vs = fma(HK::W(a, S + d), sh[S + d][x], fma(HK::W(a, d), sh[d][x], vs));
+                if (!FRZ) vs = fma(HK::W(a, S + d), sh[S + d][x], fma(HK::W(a, d), sh[d][x], vs));
             }
             wm[a] = vm; ws[a] = vs;
         }
         wm0[x] = wm[0]; wmS[x] = wm[S];
+        if (!FRZ) {
 #pragma unroll
-        for (int d = 1; d < S; ++d) {
-            const double lw = fma(lm[S + d][x], ws[S + d], lm[d][x] * ws[d]);
-            acc_ms += lw;
-            acc_dms = fma((double)d, lw, acc_dms);
-            acc_dsm = fma((double)d, fma(sh[S + d][x], wm[S + d], sh[d][x] * wm[d]), acc_dsm);
-            zds = fma((double)d, fma(z[S + d][x], sh[S + d][x], z[d][x] * sh[d][x]), zds);
+            for (int d = 1; d < S; ++d) {
+                const double lw = fma(lm[S + d][x], ws[S + d], lm[d][x] * ws[d]);
+                acc_ms += lw;
+                acc_dms = fma((double)d, lw, acc_dms);
+                acc_dsm = fma((double)d, fma(sh[S + d][x], wm[S + d], sh[d][x] * wm[d]), acc_dsm);
+                zds = fma((double)d, fma(z[S + d][x], sh[S + d][x], z[d][x] * sh[d][x]), zds);
+            }
         }
     }
     // dJ/dq_j = g_p[j] - t5_j wm_j[0] - (t5 wm[S])_{j-1}
@@ -851,7 +895,7 @@ __device__ __forceinline__ void spline_adjoint(unsigned mask, int lig, int N, in
     }
     // dJ/dT_i = partial - (1/T) sum k G_k.c_k + z.(L' s) - m^T W' s ;  L' = (d/T) L
     const double mWs = sp.t5 * sp.iT * (-(double)(2 * S - 1) * acc_ms + acc_dms + acc_dsm);
-    gT = active ? gTp + sp.iT * (zds - kGc) - mWs : 0.0;
+    gT = (active && !FRZ) ? gTp + sp.iT * (zds - kGc) - mWs : 0.0;
 }
 
 // ---- problem view ---------------------------------------------------------------------
@@ -876,11 +920,13 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // its parked optimizer state early (plain loads whose latency the adjoint then covers).
 // REP: the groups of the warp are replicas of one trajectory (latency mapping): each takes every GPW-th penalty
 // sample and the partial sums are added in replica order; replica 0 contributes the energy terms.
-template <int S, int LPT, bool PSMEM, class ST, bool REP = false, class Hook = NoHook>
+// FRZ: fixed-time specialisation (P.freeze set by the caller): the stored block factorisation is reused unless `refac`
+// (warp-uniform: some group of the warp evaluates a newly fetched problem), and nothing of dJ/dT is computed.
+template <int S, int LPT, int PSM, class ST, bool REP = false, class Hook = NoHook, bool FRZ = false>
 __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned mask, int lig, int N, int rounds,
                                                   const ProblemView &pv, const ST &store, double xt,
                                                   const double (&xq)[3], double &gt, double (&gq)[3],
-                                                  Hook before_adjoint = Hook()) {
+                                                  Hook before_adjoint = Hook(), bool refac = true) {
     constexpr int D = 2 * S, b = S - 1;
     const bool active = lig < N;
     double P0[3], P1[3], hd[b][3], td[b][3];
@@ -901,9 +947,10 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     Spline<S, LPT, ST> sp;
     sp.st = store;
     double chat[D][3];
-    spline_solve<S, LPT, ST>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat);
+    constexpr bool FS = FRZ, FT = FRZ;   // reuse of the factorisation / no time-gradient terms
+    spline_solve<S, LPT, ST, FS>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat, refac);
     double cost, G[D][3], gTp;
-    energy_partials<S, LPT, ST>(sp, chat, active, cost, G, gTp);
+    energy_partials<S, LPT, ST, FT>(sp, chat, active, cost, G, gTp);
     const int rep = REP ? Lanes<LPT>::giw() : 0;
     if (REP && rep != 0) {
         cost = 0.0; gTp = 0.0;
@@ -913,8 +960,8 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
             for (int x = 0; x < 3; ++x) G[k][x] = 0.0;
     }
     if (P.penalties && active)
-        penalty_piece<S, LPT, PSMEM, REP, ST>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, rep, Lanes<LPT>::GPW,
-                                              cost, G, gTp);
+        penalty_piece<S, LPT, PSM, REP, ST, FT>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, rep, Lanes<LPT>::GPW,
+                                                cost, G, gTp);
     if (REP) {
         cost = replica_sum<LPT>(mask, cost);
         gTp = replica_sum<LPT>(mask, gTp);
@@ -925,9 +972,12 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     }
     before_adjoint();
     double gT;
-    spline_adjoint<S, LPT, ST>(mask, lig, N, rounds, sp, G, gTp, gq, gT);
+    spline_adjoint<S, LPT, ST, FT>(mask, lig, N, rounds, sp, G, gTp, gq, gT);
     if (active) cost += P.rho * T;
-    gt = (active && !P.freeze) ? backward_grad_t(xt, gT + P.rho) : 0.0;   // freeze: durations are data, not variables
+    // freeze: durations are data, not variables.  Deliberately a run-time test also in the FRZ instantiation (where it is
+    // always true): with a compile-time zero the compiler folds it into the L-BFGS dot products and contracts them
+    // differently, and the fixed-time kernel would no longer reproduce the generic kernel bit for bit (measured).
+    gt = (active && !P.freeze) ? backward_grad_t(xt, gT + P.rho) : 0.0;
     return group_sum<LPT>(mask, cost);
 }
 

@@ -906,3 +906,27 @@ def test_overlapped_upload_gives_the_same_results(handles):
     f2, g2 = mb.evaluate(pbs[0].x0())
     np.testing.assert_array_equal(f, f2); np.testing.assert_array_equal(g, g2)
     mb.set_params(default_params(3))
+
+
+@pytest.mark.parametrize("S,N,K,B", [(3, 5, 16, 12000), (3, 8, 16, 9000), (4, 8, 16, 130), (3, 16, 16, 64), (3, 5, 50, 90), (3, 2, 8, 33), (3, 1, 8, 20)])
+def test_fixed_time_kernel_equals_generic_kernel(handles, S, N, K, B, monkeypatch):
+    """The fixed-time specialisation (optimize_kernel<.., FRZ = true>: block factorisation computed once per problem,
+    no time gradient) against the generic kernel run with DevParams::freeze (MINCOB_NO_FRZ in the environment): every
+    output bit-identical, both mappings.  Batches larger than the resident groups, so lane groups fetch new problems
+    while their warp-mates are mid-run (the warp then refactorises as a whole)."""
+    pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=(K == 50))
+    mb = handles[S]
+    for mp in (P.MAP_THROUGHPUT, P.MAP_LATENCY):
+        prm = default_params(S, flags=P.FLAG_FREEZE_TIMES, mapping=mp, max_iterations=60)
+        mb.set_params(prm)
+        mb.set_problems(pb)
+        monkeypatch.delenv("MINCOB_NO_FRZ", raising=False)
+        a = mb.optimize(pb.x0())
+        monkeypatch.setenv("MINCOB_NO_FRZ", "1")
+        b = mb.optimize(pb.x0())
+        monkeypatch.delenv("MINCOB_NO_FRZ", raising=False)
+        for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"mapping {mp} {k}")
+        if N > 1:   # (one piece: no free waypoint, nothing to iterate on in the fixed-time mode)
+            assert np.median(a["iters"]) >= 10
+    mb.set_params(default_params(S))
