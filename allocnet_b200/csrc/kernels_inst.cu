@@ -313,7 +313,8 @@ static OptPlan plan_optimize(int sm_count, const DevParams &dp, const BatchArgs 
     }
     if (per_sm < 1) { pl.code = MINCOB_E_INVALID; return pl; }
     pl.blocks = per_sm * sm_count;
-    pl.rep = can_rep && (dp.mapping == MINCOB_MAP_LATENCY || (dp.mapping == MINCOB_MAP_AUTO && a.B <= pl.blocks * WARPS));
+    // (the latency mapping keeps one flag bit per penalty sample: kappa <= 31, else the throughput mapping runs)
+    pl.rep = can_rep && dp.kappa <= 31 && (dp.mapping == MINCOB_MAP_LATENCY || (dp.mapping == MINCOB_MAP_AUTO && a.B <= pl.blocks * WARPS));
     if (pl.rep) {
         per_sm = blocks_per_sm(pick_kernel(pl.psmem, dp.mem, true, frz), pl.smem, pl.err);
         if (pl.err != cudaSuccess) return pl;

@@ -129,16 +129,21 @@ __device__ __forceinline__ double group_max(unsigned m, double v) {
         return s;
     }
 }
-// Latency mapping ("one warp per trajectory"): the GPW groups of a warp hold the SAME trajectory and split the
-// penalty samples among them; this adds up their partial sums in replica order, so that every replica ends with
-// the same bits and the replicated optimizer states never diverge.
+// Latency mapping ("one warp per trajectory"): the GPW groups of a warp hold the SAME trajectory and split the tests of
+// the penalty samples among them; this ORs a flag word over the replicas (same lane-in-group), result on every replica.
 template <int LPT>
-__device__ __forceinline__ double replica_sum(unsigned m, double v) {
-    const int l0 = Lanes<LPT>::lig();
-    double s = __shfl_sync(m, v, l0);
+__device__ __forceinline__ unsigned replica_or(unsigned m, unsigned v) {
+    if constexpr (Lanes<LPT>::POW2) {
 #pragma unroll
-    for (int r = 1; r < Lanes<LPT>::GPW; ++r) s += __shfl_sync(m, v, r * LPT + l0);
-    return s;
+        for (int o = LPT; o < 32; o <<= 1) v |= __shfl_xor_sync(m, v, o);
+        return v;
+    } else {
+        const int l0 = Lanes<LPT>::lig();
+        unsigned s = 0u;
+#pragma unroll
+        for (int r = 0; r < Lanes<LPT>::GPW; ++r) s |= __shfl_sync(m, v, r * LPT + l0);
+        return s;   // (the lanes of the dummy group read some real lane's words; they never own a piece)
+    }
 }
 
 // tau <-> T (upstream gcopter.hpp forwardT / backwardGradT)
@@ -152,11 +157,15 @@ __device__ __forceinline__ double backward_grad_t(double tau, double gradT) {
 }
 // smoothedL1, gcopter/firi.hpp:60-84; caller guarantees x > 0.
 // imu = 1/mu (hoisted: an fp64 division is ~30 instructions).
+// Every sum of a product is written as an explicit fma or __dadd_rn here and in the penalty code below (plain `*` only
+// where the product feeds another product or the multiplicand of an fma): the compiler is then left no choice of
+// contraction, so that the copies of this code in different instantiations (the two mappings, the fixed-time kernel)
+// produce the same bits.
 __device__ __forceinline__ void smoothed_l1_pos(double mu, double imu, double x, double &f, double &df) {
-    if (x > mu) { f = x - 0.5 * mu; df = 1.0; return; }
-    const double r = x * imu, r2 = r * r, h = mu - 0.5 * x;
-    f = h * r2 * r;
-    df = r2 * (-0.5 * r + 3.0 * h * imu);
+    if (x > mu) { f = fma(-0.5, mu, x); df = 1.0; return; }
+    const double r = (x * imu), r2 = (r * r), h = fma(-0.5, x, mu);
+    f = ((h * r2) * r);
+    df = (r2 * fma((3.0 * h), imu, (-0.5 * r)));
 }
 
 // ---- small dense helpers (b = S-1 = 2 or 3) ---------------------------------------------
@@ -577,6 +586,119 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
     return r;
 }
 
+// Kinematics of one penalty sample: powers of the local time s and the first three derivatives.
+template <int S>
+__device__ __forceinline__ void sample_kinematics(const double (&c)[2 * S][3], double s, double (&pw)[2 * S], double (&vel)[3],
+                                                  double (&acc)[3], double (&jer)[3]) {
+    constexpr int D = 2 * S;
+    // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
+    pw[0] = 1.0;
+#pragma unroll
+    for (int k = 1; k < D; ++k) pw[k] = (pw[k - 1] * s);
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        double v = 0.0, a = 0.0, jr = 0.0;
+#pragma unroll
+        for (int k = 1; k < D; ++k) v = fma((cfall(k, 1) * pw[k - 1]), c[k][x], v);
+#pragma unroll
+        for (int k = 2; k < D; ++k) a = fma((cfall(k, 2) * pw[k - 2]), c[k][x], a);
+#pragma unroll
+        for (int k = 3; k < D; ++k) jr = fma((cfall(k, 3) * pw[k - 3]), c[k][x], jr);
+        vel[x] = v; acc[x] = a; jer[x] = jr;
+    }
+}
+// |v|^2 - v_max^2 and friends (> 0: the hinge is active)
+__device__ __forceinline__ double excess(const double (&u)[3], double lim2) {
+    return fma(u[2], u[2], fma(u[1], u[1], fma(u[0], u[0], -lim2)));
+}
+
+// Contribution of ONE active penalty sample j to cost, dF/dc (G) and the partial dF/dT (gT): the hinges, their
+// gradients and the chain rule through the sample's bases.  hp: some half-plane test of this sample was not strictly
+// negative in phase 1; pm0/pm1: rows to re-test exactly (any superset of the rows that can be positive).
+// This is the only place where the penalty accumulates, one sample after the other in ascending j -- in both mappings.
+template <int S, int PSM, bool FRZ>
+__device__ __forceinline__ void sample_body(const DevParams &P, const double (&c)[2 * S][3], const double *planes, int rstride,
+                                            unsigned pm0, unsigned pm1, bool hp, int j, int kap, double ikap, double imu,
+                                            double step, const double (&pw)[2 * S], const double (&vel)[3],
+                                            const double (&acc)[3], const double (&jer)[3], double vv, double aa, double jj2,
+                                            double &cost, double (&G)[2 * S][3], double &gT) {
+    constexpr int D = 2 * S;
+    double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
+    double fv, df;
+    if (hp) {
+        double pos[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = D - 1; k >= 0; --k) v = fma(pw[k], c[k][x], v);
+            pos[x] = v;
+        }
+        // only rows flagged for this block (in row order, as the reference sums them)
+#pragma unroll 1
+        for (int w = 0; w < 2; ++w) {
+            unsigned todo = w ? pm1 : pm0;
+#pragma unroll 1
+            while (todo != 0u) {
+                const int k = 32 * w + __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const Plane h = load_plane<PSM == 1>(planes + (size_t)k * rstride);
+                const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
+                if (v > 0.0) {
+                    smoothed_l1_pos(P.mu, imu, v, fv, df);
+                    const double wd = (P.w_pos * df);
+                    gP[0] = fma(wd, h.x, gP[0]); gP[1] = fma(wd, h.y, gP[1]); gP[2] = fma(wd, h.z, gP[2]);
+                    pena = fma(P.w_pos, fv, pena);
+                }
+            }
+        }
+    }
+    if (vv > 0.0) {
+        smoothed_l1_pos(P.mu, imu, vv, fv, df);
+        const double wd = ((P.w_vel * df) * 2.0);
+        gV[0] = (wd * vel[0]); gV[1] = (wd * vel[1]); gV[2] = (wd * vel[2]);
+        pena = fma(P.w_vel, fv, pena);
+    }
+    if (aa > 0.0) {
+        smoothed_l1_pos(P.mu, imu, aa, fv, df);
+        const double wd = ((P.w_acc * df) * 2.0);
+        gA[0] = (wd * acc[0]); gA[1] = (wd * acc[1]); gA[2] = (wd * acc[2]);
+        pena = fma(P.w_acc, fv, pena);
+    }
+    if (jj2 > 0.0) {
+        smoothed_l1_pos(P.mu, imu, jj2, fv, df);
+        const double wd = ((P.w_jerk * df) * 2.0);
+        gJ[0] = (wd * jer[0]); gJ[1] = (wd * jer[1]); gJ[2] = (wd * jer[2]);
+        pena = fma(P.w_jerk, fv, pena);
+    }
+    const double node = (j == 0 || j == kap) ? 0.5 : 1.0;
+    const double w = (node * step);
+    double dsum = 0.0;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+        if (!FRZ) {
+            double sn = 0.0;
+#pragma unroll
+            for (int k = 4; k < D; ++k) sn = fma((cfall(k, 4) * pw[k - 4]), c[k][x], sn);
+            dsum = fma(gJ[x], sn, fma(gA[x], jer[x], fma(gV[x], acc[x], fma(gP[x], vel[x], dsum))));
+        }
+        const double wP = (w * gP[x]), wV = (w * gV[x]), wA = (w * gA[x]), wJ = (w * gJ[x]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double t = (pw[k] * wP);
+            if (k >= 1) t = fma((cfall(k, 1) * pw[k - 1]), wV, t);
+            if (k >= 2) t = fma((cfall(k, 2) * pw[k - 2]), wA, t);
+            if (k >= 3) t = fma((cfall(k, 3) * pw[k - 3]), wJ, t);
+            G[k][x] = __dadd_rn(G[k][x], t);
+        }
+    }
+    if (!FRZ) {
+        const double through_t = ((dsum * ((double)j * ikap)) * w);
+        gT = __dadd_rn(gT, fma((node * pena), ikap, through_t));
+    }
+    cost = fma(w, pena, cost);
+}
+
 // attachPenaltyFunctional for this piece.  planes: this piece's rows.
 // Phase 1 tests a register block of JB sample positions against every half-plane, so each row is
 // loaded once per block instead of once per sample.  Phase 2 is a ROLLED loop over the samples of
@@ -584,22 +706,27 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
 // loop has to stay inside the 32 KB instruction cache.
 // Rows touched by a block are remembered in a 64-bit mask (two words: the second one is only ever written when
 // K > 32, e.g. the reference's polytopes padded to 50 rows, learning_planner.hpp:40,157-168); K <= MINCOB_MAX_ROWS = 64.
-// REP (latency mapping): this lane evaluates only the samples j = jbase + u * jstride; the caller adds the
-// replicas' partial sums.  REP = false: every sample, in order.
+// REP (latency mapping, all lanes of the warp call this, `live` = the lane holds a piece): the replicas split the TESTS --
+// this lane runs phase 1 and the hinge tests of the samples j = jbase + u * jstride only and records which of them are
+// active; the flag words are ORed over the replicas, and then EVERY replica accumulates the active samples itself, in
+// ascending j like the throughput mapping (sample_body; the replicas hold the same coefficients, so nothing but flags
+// is exchanged).  The sums are therefore bit-identical to REP = false, and the replicas stay bit-identical to each other.
+// Needs kappa <= 31 (one flag bit per sample; the launcher checks).
 // PSM: where the rows are.  0: global memory (C-ABI layout); 1: the group's shared-memory stage.  (A hybrid -- the
 // first rows of polytopes too large to stage whole in the stage, the rest in global memory -- was built and measured in
 // round 2: no gain at any split, profiles/r02_tail_experiments.md section 7.)
 // FRZ (fixed-time mode): the time-gradient terms (through the sample times and the quadrature weights) are not computed.
 template <int S, int LPT, int PSM, bool REP, class ST, bool FRZ = false>
 __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S, LPT, ST> &sp, const double *planes,
-                                              int rstride, int K, int jbase, int jstride, double &cost,
+                                              int rstride, int K, bool live, int jbase, int jstride, double &cost,
                                               double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S, JB = MINCOB_JB;
     const int kap = P.kappa;
     const double ikap = P.ikap, imu = P.imu;
     const double step = sp.T * ikap;
-    const int cnt = REP ? (jbase <= kap ? (kap - jbase) / jstride + 1 : 0) : kap + 1;   // samples of this lane
+    const int cnt = REP ? ((live && jbase <= kap) ? (kap - jbase) / jstride + 1 : 0) : kap + 1;   // samples this lane tests
     auto sample = [&](int u) { return REP ? jbase + u * jstride : u; };
+    unsigned need = 0u, hitj = 0u, rm0 = 0u, rm1 = 0u;   // REP: active samples / samples with a flagged row (bit j), flagged rows
 #pragma unroll 1
     for (int j0 = 0; j0 < cnt; j0 += JB) {
         unsigned hit = 0u, pm0 = 0u, pm1 = 0u;
@@ -614,7 +741,8 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             double pos[JB][3];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
-                const double s = sample(j0 + jj) * step;
+                // (slots past this lane's last sample repeat it: a position beyond the end of the piece would flag rows)
+                const double s = sample(min(j0 + jj, cnt - 1)) * step;
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                     double v = sp.c[D - 1][x];
@@ -668,99 +796,41 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
         for (int jj = 0; jj < jend; ++jj) {
             const int j = sample(j0 + jj);
             const double s = j * step;
-            // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
-            double pw[D];
-            pw[0] = 1.0;
-#pragma unroll
-            for (int k = 1; k < D; ++k) pw[k] = pw[k - 1] * s;
-            double vel[3], acc[3], jer[3];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                double v = 0.0, a = 0.0, jr = 0.0;
-#pragma unroll
-                for (int k = 1; k < D; ++k) v = fma(cfall(k, 1) * pw[k - 1], sp.c[k][x], v);
-#pragma unroll
-                for (int k = 2; k < D; ++k) a = fma(cfall(k, 2) * pw[k - 2], sp.c[k][x], a);
-#pragma unroll
-                for (int k = 3; k < D; ++k) jr = fma(cfall(k, 3) * pw[k - 3], sp.c[k][x], jr);
-                vel[x] = v; acc[x] = a; jer[x] = jr;
-            }
-            const double vv = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - P.vmax2;
-            const double aa = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] - P.amax2;
-            const double jj2 = jer[0] * jer[0] + jer[1] * jer[1] + jer[2] * jer[2] - P.jmax2;
+            double pw[D], vel[3], acc[3], jer[3];
+            sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);
+            const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2), jj2 = excess(jer, P.jmax2);
             const bool hp = (hit >> jj) & 1u;
             if (hp || vv > 0.0 || aa > 0.0 || jj2 > 0.0) {
-                double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
-                double fv, df;
-                if (hp) {
-                    double pos[3];
-#pragma unroll
-                    for (int x = 0; x < 3; ++x) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int k = D - 1; k >= 0; --k) v = fma(pw[k], sp.c[k][x], v);
-                        pos[x] = v;
-                    }
-                    // only rows flagged for this block (in row order, as the reference sums them)
+                if constexpr (REP) {
+                    need |= 1u << j;
+                    hitj |= (hp ? 1u : 0u) << j;
+                } else {
+                    sample_body<S, PSM, FRZ>(P, sp.c, planes, rstride, pm0, pm1, hp, j, kap, ikap, imu, step, pw, vel, acc, jer,
+                                             vv, aa, jj2, cost, G, gT);
+                }
+            }
+        }
+        if constexpr (REP) { rm0 |= pm0; rm1 |= pm1; }
+    }
+    if constexpr (REP) {
+        constexpr unsigned FULL = 0xffffffffu;
+        need = replica_or<LPT>(FULL, need);
+        hitj = replica_or<LPT>(FULL, hitj);
+        rm0 = replica_or<LPT>(FULL, rm0);
+        rm1 = replica_or<LPT>(FULL, rm1);
+        if (!live) need = 0u;
+        unsigned todo = __reduce_or_sync(FULL, need);   // samples some piece of the trajectory has active (warp-uniform)
 #pragma unroll 1
-                    for (int w = 0; w < 2; ++w) {
-                        unsigned todo = w ? pm1 : pm0;
-#pragma unroll 1
-                        while (todo != 0u) {
-                            const int k = 32 * w + __ffs(todo) - 1;
-                            todo &= todo - 1u;
-                            const Plane h = load_plane<PSM == 1>(planes + (size_t)k * rstride);
-                            const double v = fma(h.x, pos[0], fma(h.y, pos[1], fma(h.z, pos[2], h.w)));
-                            if (v > 0.0) {
-                                smoothed_l1_pos(P.mu, imu, v, fv, df);
-                                const double wd = P.w_pos * df;
-                                gP[0] += wd * h.x; gP[1] += wd * h.y; gP[2] += wd * h.z;
-                                pena += P.w_pos * fv;
-                            }
-                        }
-                    }
-                }
-                if (vv > 0.0) {
-                    smoothed_l1_pos(P.mu, imu, vv, fv, df);
-                    const double wd = P.w_vel * df * 2.0;
-                    gV[0] = wd * vel[0]; gV[1] = wd * vel[1]; gV[2] = wd * vel[2];
-                    pena += P.w_vel * fv;
-                }
-                if (aa > 0.0) {
-                    smoothed_l1_pos(P.mu, imu, aa, fv, df);
-                    const double wd = P.w_acc * df * 2.0;
-                    gA[0] = wd * acc[0]; gA[1] = wd * acc[1]; gA[2] = wd * acc[2];
-                    pena += P.w_acc * fv;
-                }
-                if (jj2 > 0.0) {
-                    smoothed_l1_pos(P.mu, imu, jj2, fv, df);
-                    const double wd = P.w_jerk * df * 2.0;
-                    gJ[0] = wd * jer[0]; gJ[1] = wd * jer[1]; gJ[2] = wd * jer[2];
-                    pena += P.w_jerk * fv;
-                }
-                const double node = (j == 0 || j == kap) ? 0.5 : 1.0;
-                const double w = node * step;
-                double dsum = 0.0;
-#pragma unroll
-                for (int x = 0; x < 3; ++x) {
-                    if (!FRZ) {
-                        double sn = 0.0;
-#pragma unroll
-                        for (int k = 4; k < D; ++k) sn = fma(cfall(k, 4) * pw[k - 4], sp.c[k][x], sn);
-                        dsum += gP[x] * vel[x] + gV[x] * acc[x] + gA[x] * jer[x] + gJ[x] * sn;
-                    }
-                    const double wP = w * gP[x], wV = w * gV[x], wA = w * gA[x], wJ = w * gJ[x];
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        double t = pw[k] * wP;
-                        if (k >= 1) t = fma(cfall(k, 1) * pw[k - 1], wV, t);
-                        if (k >= 2) t = fma(cfall(k, 2) * pw[k - 2], wA, t);
-                        if (k >= 3) t = fma(cfall(k, 3) * pw[k - 3], wJ, t);
-                        G[k][x] += t;
-                    }
-                }
-                if (!FRZ) gT += dsum * (j * ikap) * w + node * pena * ikap;
-                cost += w * pena;
+        while (todo != 0u) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            if ((need >> j) & 1u) {
+                const double s = j * step;
+                double pw[D], vel[3], acc[3], jer[3];
+                sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);
+                const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2), jj2 = excess(jer, P.jmax2);
+                sample_body<S, PSM, FRZ>(P, sp.c, planes, rstride, rm0, rm1, (hitj >> j) & 1u, j, kap, ikap, imu, step, pw, vel,
+                                         acc, jer, vv, aa, jj2, cost, G, gT);
             }
         }
     }
@@ -918,8 +988,9 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 // `before_adjoint` runs between the penalty loop and the adjoint: the optimize kernel uses it to request
 // its parked optimizer state early (plain loads whose latency the adjoint then covers).
-// REP: the groups of the warp are replicas of one trajectory (latency mapping): each takes every GPW-th penalty
-// sample and the partial sums are added in replica order; replica 0 contributes the energy terms.
+// REP: the groups of the warp are replicas of one trajectory (latency mapping): each tests every GPW-th penalty sample,
+// the flags are exchanged, and every replica accumulates the active samples in ascending order (penalty_piece): the
+// result has the bits of the throughput mapping.
 // FRZ: fixed-time specialisation (P.freeze set by the caller): the stored block factorisation is reused unless `refac`
 // (warp-uniform: some group of the warp evaluates a newly fetched problem), and nothing of dJ/dT is computed.
 template <int S, int LPT, int PSM, class ST, bool REP = false, class Hook = NoHook, bool FRZ = false>
@@ -951,29 +1022,21 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
     spline_solve<S, LPT, ST, FS>(mask, lig, N, rounds, T, P0, P1, hd, td, sp, chat, refac);
     double cost, G[D][3], gTp;
     energy_partials<S, LPT, ST, FT>(sp, chat, active, cost, G, gTp);
-    const int rep = REP ? Lanes<LPT>::giw() : 0;
-    if (REP && rep != 0) {
-        cost = 0.0; gTp = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-#pragma unroll
-            for (int x = 0; x < 3; ++x) G[k][x] = 0.0;
-    }
-    if (P.penalties && active)
-        penalty_piece<S, LPT, PSM, REP, ST, FT>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, rep, Lanes<LPT>::GPW,
-                                                cost, G, gTp);
-    if (REP) {
-        cost = replica_sum<LPT>(mask, cost);
-        gTp = replica_sum<LPT>(mask, gTp);
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-#pragma unroll
-            for (int x = 0; x < 3; ++x) G[k][x] = replica_sum<LPT>(mask, G[k][x]);
+    // (REP: every replica computes the energy terms itself and accumulates the same active samples in the same order:
+    // nothing to add up afterwards)
+    if (P.penalties) {
+        if constexpr (REP) {
+            penalty_piece<S, LPT, PSM, true, ST, FT>(P, sp, pv.planes, pv.rstride, (active && pv.planes) ? pv.rows : 0, active,
+                                                     Lanes<LPT>::giw(), Lanes<LPT>::GPW, cost, G, gTp);
+        } else if (active) {
+            penalty_piece<S, LPT, PSM, false, ST, FT>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, true, 0, 1,
+                                                      cost, G, gTp);
+        }
     }
     before_adjoint();
     double gT;
     spline_adjoint<S, LPT, ST, FT>(mask, lig, N, rounds, sp, G, gTp, gq, gT);
-    if (active) cost += P.rho * T;
+    if (active) cost = fma(P.rho, T, cost);
     // freeze: durations are data, not variables.  Deliberately a run-time test also in the FRZ instantiation (where it is
     // always true): with a compile-time zero the compiler folds it into the L-BFGS dot products and contracts them
     // differently, and the fixed-time kernel would no longer reproduce the generic kernel bit for bit (measured).

@@ -149,13 +149,15 @@ def test_cost_functional_near_optimum(handles, oracle):
     assert float(np.max(np.abs(f - fo) / np.abs(fo))) <= TOL
     rng = np.random.default_rng(7)
     sens = np.zeros(x.shape[0])
-    for _ in range(4):
+    for _ in range(12):   # (the sensitivity is a maximum over perturbations: a handful of draws underestimates it)
         xp = x * (1.0 + 1e-15 * np.sign(rng.normal(size=x.shape)))
         _, g2 = oracle.cost_batch(prm, pb, xp, nthreads=8)
         sens = np.maximum(sens, np.abs(g2 - go).max(axis=1))
     err = np.abs(g - go).max(axis=1)
     bound = np.maximum(TOL * np.abs(go).max(axis=1), 4.0 * sens)
-    assert (err <= bound).all(), (float((err / bound).max()), int((err > bound).sum()))
+    ratio = err / bound
+    print("near-optimum gradient: worst err/bound", float(ratio.max()), "over the bound:", int((ratio > 1).sum()), "of", len(ratio))
+    assert (err <= bound).all(), (float(ratio.max()), int((err > bound).sum()))
     assert np.median(err / np.maximum(np.abs(go).max(axis=1), 1e-300)) <= TOL   # typical problem: plain 1e-9
 
 
@@ -626,10 +628,10 @@ def test_gradient_norm_stop(handles, oracle):
 @pytest.mark.parametrize("S,N,K,B", [(3, 8, 16, 96), (3, 5, 16, 50), (3, 16, 16, 40), (4, 8, 16, 33), (3, 5, 50, 31),
                                      (3, 3, 7, 20), (3, 8, 0, 40)])
 def test_latency_mapping_follows_the_throughput_mapping(handles, oracle, S, N, K, B):
-    """MINCOB_MAP_LATENCY (the lane groups of a warp share one trajectory and split the penalty samples) runs the same
-    state machine on the same numbers up to the summation order of the samples: after a few iterations both mappings
-    report the same status / iteration / evaluation counts and the same iterate (1e-7, as the oracle trace test), and
-    full runs end at points where the reported cost is the oracle's cost to 1e-9."""
+    """MINCOB_MAP_LATENCY (the lane groups of a warp share one trajectory and split the TESTS of the penalty samples; every
+    replica then accumulates the active samples in ascending order, like the throughput mapping) gives the bits of
+    MINCOB_MAP_THROUGHPUT: every output of full runs identical, and the reported cost is the oracle's cost at the final x
+    to 1e-9.  (Until round 2 the replicas added partial sums and the mappings agreed to rounding only.)"""
     pb = synth.make_problems(B, N=N, K=K, S=S, ragged_rows=(K == 50))
     mb = handles[S]
     mb.set_problems(pb)
@@ -643,11 +645,10 @@ def test_latency_mapping_follows_the_throughput_mapping(handles, oracle, S, N, K
             mb.set_params(prm)
             out[it, mp] = mb.optimize(pb.x0())
             assert mb.last_mapping() == (mp if N <= 16 else P.MAP_THROUGHPUT)
-    a, b = out[3, P.MAP_THROUGHPUT], out[3, P.MAP_LATENCY]
-    same = (a["evals"] == b["evals"]) & (a["iters"] == b["iters"]) & (a["status"] == b["status"])
-    assert same.mean() >= 0.97, same.mean()
-    assert rel_rows(a["x"][same], b["x"][same]) <= 1e-7
-    assert float(np.max(np.abs(a["f"][same] - b["f"][same]) / np.abs(b["f"][same]))) <= 1e-7
+    for it in (3, 0):
+        a, b = out[it, P.MAP_THROUGHPUT], out[it, P.MAP_LATENCY]
+        for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"max_iterations {it}: {k}")
     full = out[0, P.MAP_LATENCY]
     assert ((full["status"] >= 0) | (full["status"] == P.LBFGSERR_MAXIMUMITERATION)).all()
     fo, _ = oracle.cost_batch(base, pb, full["x"], nthreads=8)
@@ -655,8 +656,6 @@ def test_latency_mapping_follows_the_throughput_mapping(handles, oracle, S, N, K
     # coefficients written by replica 0 are the trajectory at the final x
     T = synth.forward_t(full["x"][:, :N])
     np.testing.assert_allclose(full["T"], T, rtol=1e-14)
-    rel = np.abs(full["f"] - out[0, P.MAP_THROUGHPUT]["f"]) / np.abs(full["f"])
-    assert np.median(rel) <= 5e-3
     mb.set_params(default_params(S))
 
 
