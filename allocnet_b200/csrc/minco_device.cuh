@@ -756,18 +756,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             auto scan = [&](auto in_smem, const double *base, int stride, int ka, int kb, unsigned &pm) {
                 constexpr bool SM = decltype(in_smem)::value;
                 constexpr int UK = SM ? MINCOB_UNROLL_K : MINCOB_UNROLL_KG;
-#if MINCOB_PLANE_PREFETCH
-                // software pipelining by one row: the next row's load is in flight while this row's tests issue
-                Plane hnext = load_plane<SM>(base + (size_t)(ka < kb ? ka : 0) * stride);
-#endif
-#pragma unroll UK
-                for (int k = ka; k < kb; ++k) {
-#if MINCOB_PLANE_PREFETCH
-                    const Plane h = hnext;
-                    hnext = load_plane<SM>(base + (size_t)(k + 1 < kb ? k + 1 : k) * stride);
-#else
-                    const Plane h = load_plane<SM>(base + (size_t)k * stride);
-#endif
+                auto test_row = [&](const Plane &h, unsigned bit) {
                     int all = -1;
 #pragma unroll
                     for (int jj = 0; jj < JB; ++jj) {
@@ -775,8 +764,37 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                         keep[jj] &= __double2hiint(v);
                         all &= __double2hiint(v);
                     }
-                    pm |= (all < 0 ? 0u : 1u) << (k & 31);   // row k touched by some sample of the block
+                    pm |= all < 0 ? 0u : bit;   // row touched by some sample of the block
+                };
+#if MINCOB_PLANE_PREFETCH
+                if constexpr (SM) {
+                    // software pipelining by one row: the next row's load is in flight while this row's tests issue.  In
+                    // the stage the row after a polytope's last one is still inside the group's shared memory (the next
+                    // rows or the small arrays behind the stage), so the pointer just advances: no clamp, no multiply.
+                    const double *p = base + (size_t)ka * stride;
+                    Plane hnext = load_plane<true>(p);
+                    unsigned bit = 1u << (ka & 31);
+#pragma unroll UK
+                    for (int k = ka; k < kb; ++k) {
+                        const Plane h = hnext;
+                        p += stride;
+                        hnext = load_plane<true>(p);
+                        test_row(h, bit);
+                        bit <<= 1;
+                    }
+                } else {
+                    Plane hnext = load_plane<false>(base + (size_t)(ka < kb ? ka : 0) * stride);
+#pragma unroll UK
+                    for (int k = ka; k < kb; ++k) {
+                        const Plane h = hnext;
+                        hnext = load_plane<false>(base + (size_t)(k + 1 < kb ? k + 1 : k) * stride);
+                        test_row(h, 1u << (k & 31));
+                    }
                 }
+#else
+#pragma unroll UK
+                for (int k = ka; k < kb; ++k) test_row(load_plane<SM>(base + (size_t)k * stride), 1u << (k & 31));
+#endif
             };
 #pragma unroll 1
             for (int k0 = 0; k0 < K; k0 += 32) {      // one mask word per trip; a single trip unless K > 32
