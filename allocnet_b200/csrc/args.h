@@ -33,6 +33,7 @@ struct DevParams {
     int kappa;
     double mu, w_pos, w_vel, w_acc, w_jerk, vmax2, amax2, jmax2, rho;
     double imu, ikap;   // 1/mu, 1/kappa (an fp64 division is ~30 instructions on the device)
+    double amax2q;      // amax2 / 4 (exact): the sample loop tests half the acceleration (minco_device.cuh::sample_kinematics)
     int penalties;  // 0: energy-only fast path (all weights zero)
     int mapping;    // MINCOB_MAP_AUTO / _THROUGHPUT / _LATENCY (include/mincob.h)
     int freeze;     // 1: MINCOB_FLAG_FREEZE_TIMES -- durations stay as given (d/dtau = 0), waypoints only

@@ -586,10 +586,13 @@ __device__ __forceinline__ Plane load_plane(const double *p) {
     return r;
 }
 
-// Kinematics of one penalty sample: powers of the local time s and the first three derivatives.
+// Kinematics of one penalty sample: powers of the local time s and the first three derivatives.  The chains start from
+// their first term (c_1, c_2, 6 c_3) instead of from zero, and the acceleration is carried as HALF its value
+// (hacc = c_2 + 3 s c_3 + 6 s^2 c_4 + ...): scaling by two commutes with every rounding, so 2 * hacc has the bits of the
+// directly accumulated sum, and the sample loop saves the doubling (sample_body undoes it for the rare active sample).
 template <int S>
 __device__ __forceinline__ void sample_kinematics(const double (&c)[2 * S][3], double s, double (&pw)[2 * S], double (&vel)[3],
-                                                  double (&acc)[3], double (&jer)[3]) {
+                                                  double (&hacc)[3], double (&jer)[3]) {
     constexpr int D = 2 * S;
     // derivative bases: bd[k] = k!/(k-d)! s^(k-d)
     pw[0] = 1.0;
@@ -597,14 +600,14 @@ __device__ __forceinline__ void sample_kinematics(const double (&c)[2 * S][3], d
     for (int k = 1; k < D; ++k) pw[k] = (pw[k - 1] * s);
 #pragma unroll
     for (int x = 0; x < 3; ++x) {
-        double v = 0.0, a = 0.0, jr = 0.0;
+        double v = c[1][x], a = c[2][x], jr = 6.0 * c[3][x];
 #pragma unroll
-        for (int k = 1; k < D; ++k) v = fma((cfall(k, 1) * pw[k - 1]), c[k][x], v);
+        for (int k = 2; k < D; ++k) v = fma((cfall(k, 1) * pw[k - 1]), c[k][x], v);
 #pragma unroll
-        for (int k = 2; k < D; ++k) a = fma((cfall(k, 2) * pw[k - 2]), c[k][x], a);
+        for (int k = 3; k < D; ++k) a = fma(((0.5 * cfall(k, 2)) * pw[k - 2]), c[k][x], a);
 #pragma unroll
-        for (int k = 3; k < D; ++k) jr = fma((cfall(k, 3) * pw[k - 3]), c[k][x], jr);
-        vel[x] = v; acc[x] = a; jer[x] = jr;
+        for (int k = 4; k < D; ++k) jr = fma((cfall(k, 3) * pw[k - 3]), c[k][x], jr);
+        vel[x] = v; hacc[x] = a; jer[x] = jr;
     }
 }
 // |v|^2 - v_max^2 and friends (> 0: the hinge is active)
@@ -620,9 +623,12 @@ template <int S, int PSM, bool FRZ>
 __device__ __forceinline__ void sample_body(const DevParams &P, const double (&c)[2 * S][3], const double *planes, int rstride,
                                             unsigned pm0, unsigned pm1, bool hp, int j, int kap, double ikap, double imu,
                                             double step, const double (&pw)[2 * S], const double (&vel)[3],
-                                            const double (&acc)[3], const double (&jer)[3], double vv, double aa, double jj2,
+                                            const double (&hacc)[3], const double (&jer)[3], double vv, double aa4, double jj2,
                                             double &cost, double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S;
+    // sample_kinematics carries half the acceleration and the caller a quarter of its excess: exact to undo
+    const double acc[3] = {2.0 * hacc[0], 2.0 * hacc[1], 2.0 * hacc[2]};
+    const double aa = 4.0 * aa4;
     double pena = 0.0, gP[3] = {0, 0, 0}, gV[3] = {0, 0, 0}, gA[3] = {0, 0, 0}, gJ[3] = {0, 0, 0};
     double fv, df;
     if (hp) {
@@ -815,8 +821,9 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             const int j = sample(j0 + jj);
             const double s = j * step;
             double pw[D], vel[3], acc[3], jer[3];
-            sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);
-            const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2), jj2 = excess(jer, P.jmax2);
+            sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);   // acc: half the acceleration
+            // aa: a quarter of |a|^2 - a_max^2 (same sign, exactly a quarter of the value)
+            const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2q), jj2 = excess(jer, P.jmax2);
             const bool hp = (hit >> jj) & 1u;
             if (hp || vv > 0.0 || aa > 0.0 || jj2 > 0.0) {
                 if constexpr (REP) {
@@ -846,7 +853,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 const double s = j * step;
                 double pw[D], vel[3], acc[3], jer[3];
                 sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);
-                const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2), jj2 = excess(jer, P.jmax2);
+                const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2q), jj2 = excess(jer, P.jmax2);
                 sample_body<S, PSM, FRZ>(P, sp.c, planes, rstride, rm0, rm1, (hitj >> j) & 1u, j, kap, ikap, imu, step, pw, vel,
                                          acc, jer, vv, aa, jj2, cost, G, gT);
             }

@@ -157,6 +157,7 @@ static int derive(mincob_ctx *h) {
     d.imu = 1.0 / p.mu; d.ikap = 1.0 / p.kappa;
     d.w_pos = p.w_pos; d.w_vel = p.w_vel; d.w_acc = p.w_acc; d.w_jerk = p.w_jerk;
     d.vmax2 = p.v_max * p.v_max; d.amax2 = p.a_max * p.a_max; d.jmax2 = p.j_max * p.j_max;
+    d.amax2q = 0.25 * d.amax2;
     d.rho = p.rho;
     if (p.flags & ~(MINCOB_FLAG_FREEZE_TIMES | MINCOB_FLAG_PLANNER_ROWS)) return fail(h, MINCOB_E_INVALID, "unknown bits in flags (%d)", p.flags);
     if (p.mapping < MINCOB_MAP_AUTO || p.mapping > MINCOB_MAP_LATENCY) return fail(h, MINCOB_E_INVALID, "mapping must be MINCOB_MAP_AUTO/THROUGHPUT/LATENCY");
