@@ -44,6 +44,9 @@
 #ifndef MINCOB_UNROLL_KG
 #define MINCOB_UNROLL_KG 2   // same, when the rows are read from global memory (polytopes too large to stage)
 #endif
+#ifndef MINCOB_DEFER_BODY
+#define MINCOB_DEFER_BODY 0  // throughput mapping: accumulate the active samples after all tests, every lane its own (experiment)
+#endif
 #ifndef MINCOB_UNROLL_K
 #define MINCOB_UNROLL_K 1    // half-plane rows per trip of the phase-1 loop (2: -4 %, 4: -4 %, 8: -10 %; the kernel is code-size sensitive)
 #endif
@@ -727,10 +730,12 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                                               int rstride, int K, bool live, int jbase, int jstride, double &cost,
                                               double (&G)[2 * S][3], double &gT) {
     constexpr int D = 2 * S, JB = MINCOB_JB;
+    constexpr bool DEFER = REP || MINCOB_DEFER_BODY;   // active samples are accumulated after all tests, not inside the test loop
     const int kap = P.kappa;
     const double ikap = P.ikap, imu = P.imu;
     const double step = sp.T * ikap;
-    const int cnt = REP ? ((live && jbase <= kap) ? (kap - jbase) / jstride + 1 : 0) : kap + 1;   // samples this lane tests
+    const int cnt = REP ? ((live && jbase <= kap) ? (kap - jbase) / jstride + 1 : 0)
+                        : ((MINCOB_DEFER_BODY && !live) ? 0 : kap + 1);   // samples this lane tests
     auto sample = [&](int u) { return REP ? jbase + u * jstride : u; };
     unsigned need = 0u, hitj = 0u, rm0 = 0u, rm1 = 0u;   // REP: active samples / samples with a flagged row (bit j), flagged rows
 #pragma unroll 1
@@ -826,7 +831,7 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
             const double vv = excess(vel, P.vmax2), aa = excess(acc, P.amax2q), jj2 = excess(jer, P.jmax2);
             const bool hp = (hit >> jj) & 1u;
             if (hp || vv > 0.0 || aa > 0.0 || jj2 > 0.0) {
-                if constexpr (REP) {
+                if constexpr (DEFER) {
                     need |= 1u << j;
                     hitj |= (hp ? 1u : 0u) << j;
                 } else {
@@ -835,21 +840,23 @@ __device__ __forceinline__ void penalty_piece(const DevParams &P, const Spline<S
                 }
             }
         }
-        if constexpr (REP) { rm0 |= pm0; rm1 |= pm1; }
+        if constexpr (DEFER) { rm0 |= pm0; rm1 |= pm1; }
     }
-    if constexpr (REP) {
+    if constexpr (DEFER) {
         constexpr unsigned FULL = 0xffffffffu;
-        need = replica_or<LPT>(FULL, need);
-        hitj = replica_or<LPT>(FULL, hitj);
-        rm0 = replica_or<LPT>(FULL, rm0);
-        rm1 = replica_or<LPT>(FULL, rm1);
+        if constexpr (REP) {
+            need = replica_or<LPT>(FULL, need);
+            hitj = replica_or<LPT>(FULL, hitj);
+            rm0 = replica_or<LPT>(FULL, rm0);
+            rm1 = replica_or<LPT>(FULL, rm1);
+        }
         if (!live) need = 0u;
-        unsigned todo = __reduce_or_sync(FULL, need);   // samples some piece of the trajectory has active (warp-uniform)
+        // every lane works through ITS active samples in ascending order: the trips are the largest count of any lane
 #pragma unroll 1
-        while (todo != 0u) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            if ((need >> j) & 1u) {
+        while (__any_sync(FULL, need != 0u)) {
+            if (need != 0u) {
+                const int j = __ffs(need) - 1;
+                need &= need - 1u;
                 const double s = j * step;
                 double pw[D], vel[3], acc[3], jer[3];
                 sample_kinematics<S>(sp.c, s, pw, vel, acc, jer);
@@ -1053,6 +1060,9 @@ __device__ __forceinline__ double cost_functional(const DevParams &P, unsigned m
         if constexpr (REP) {
             penalty_piece<S, LPT, PSM, true, ST, FT>(P, sp, pv.planes, pv.rstride, (active && pv.planes) ? pv.rows : 0, active,
                                                      Lanes<LPT>::giw(), Lanes<LPT>::GPW, cost, G, gTp);
+        } else if constexpr (MINCOB_DEFER_BODY) {   // (all lanes call: the deferred accumulation loop votes over the warp)
+            penalty_piece<S, LPT, PSM, false, ST, FT>(P, sp, pv.planes, pv.rstride, (active && pv.planes) ? pv.rows : 0, active,
+                                                      0, 1, cost, G, gTp);
         } else if (active) {
             penalty_piece<S, LPT, PSM, false, ST, FT>(P, sp, pv.planes, pv.rstride, pv.planes ? pv.rows : 0, true, 0, 1,
                                                       cost, G, gTp);
