@@ -280,9 +280,8 @@ static int blocks_per_sm(OptKernel kern, size_t smem, cudaError_t &e) {
     return e == cudaSuccess ? per_sm : 0;
 }
 // mapping: MINCOB_MAP_AUTO picks the latency mapping (one warp per trajectory) when the batch cannot give every
-// resident warp a trajectory of its own anyway; the results of the two mappings agree to rounding (the penalty
-// samples are added in a different order), so a caller that needs run-to-run identical bits across batch sizes
-// pins the mapping in mincob_params.
+// resident warp a trajectory of its own anyway; the two mappings produce the same bits (penalty_piece), so the choice
+// changes timing only.
 static size_t smem_bytes(int N, int K, const DevParams &dp, int psmem) {
     return ((size_t)GPB * optimize_group_doubles(S, N, K, dp.mem, dp.past, psmem, LPT) +
             (size_t)(SPB - GPB) * optimize_small_doubles(S, dp.mem, dp.past, LPT)) * sizeof(double);

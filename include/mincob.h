@@ -92,12 +92,12 @@ typedef struct mincob_params {
 #define MINCOB_FLAG_PLANNER_ROWS 2
 /* mapping (mincob_optimize only).
  * THROUGHPUT: one lane per piece, 32/LPT trajectories per warp (LPT = 5, 8, 16 or 32 lanes for N <= 5, 8, 16, 32).
- * LATENCY: "one warp per trajectory" -- the lane groups of a warp hold the same trajectory and split the penalty
- *   samples of every piece; fewer trajectories in flight, each evaluation 2-3x shorter.  For single problems and
- *   small batches.
+ * LATENCY: "one warp per trajectory" -- the lane groups of a warp hold the same trajectory and split the tests of
+ *   the penalty samples of every piece; fewer trajectories in flight, each evaluation ~1.3x shorter.  For single
+ *   problems and small batches (needs kappa <= 31, otherwise THROUGHPUT runs).
  * AUTO: LATENCY when the batch has no more trajectories than the device holds resident warps, else THROUGHPUT.
- * The two mappings add the penalty samples in a different order: results agree to rounding, not bit for bit; for
- * a given mapping they are bit-reproducible and independent of batch composition. */
+ * The two mappings accumulate the active penalty samples in the same order with the same arithmetic: every output
+ * is bit-identical in both, reproducible from run to run and independent of what else is in the batch. */
 #define MINCOB_MAP_AUTO 0
 #define MINCOB_MAP_THROUGHPUT 1
 #define MINCOB_MAP_LATENCY 2

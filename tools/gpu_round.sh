@@ -17,9 +17,15 @@ cfg --config 4 --steps 3
 cfg --pieces 5 --steps 5
 cfg --pieces 5 --K 50 --steps 3
 cfg --pieces 5 --steps 5 --freeze-times
+cfg --steps 4 --freeze-times
+cfg --pieces 16 --steps 3 --freeze-times
+cfg --pieces 5 --K 50 --steps 3 --freeze-times
+cfg --pieces 16 --steps 3
 cfg --batch 1 --pieces 5 --steps 30 --warmup 5 --no-e2e
 cfg --batch 1 --pieces 5 --steps 30 --warmup 5 --no-e2e --mapping throughput
 cfg --batch 64 --pieces 5 --steps 30 --warmup 5 --no-e2e
+cfg --batch 1 --steps 30 --warmup 5 --no-e2e
+cfg --batch 1 --steps 30 --warmup 5 --no-e2e --mapping throughput
 cfg --S 4 --steps 3
 python - <<'PY'
 import json
