@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(THREADS, MINCOB_MINB) optimize_kernel(const De
                                         (finish && writer && a.coeffs) ? a.coeffs + (size_t)prob * N * 3 * 2 * S : nullptr,
                                         (finish && writer && a.T) ? a.T + (size_t)prob * N : nullptr);
             if (finish) phase = PH_FETCH;
+            __syncwarp();   // emit_trajectory read the group's head / tail; the fetch of the next trip overwrites them
         }
     }
     if (a.total_evals && my_evals) atomicAdd(a.total_evals, my_evals);
