@@ -929,3 +929,32 @@ def test_fixed_time_kernel_equals_generic_kernel(handles, S, N, K, B, monkeypatc
         if N > 1:   # (one piece: no free waypoint, nothing to iterate on in the fixed-time mode)
             assert np.median(a["iters"]) >= 10
     mb.set_params(default_params(S))
+
+
+@pytest.mark.parametrize("kappa", [1, 5, 6, 7, 13, 31, 32, 40])
+def test_integral_intervals(handles, oracle, kappa):
+    """IntegralIntervs (kappa sub-intervals, kappa + 1 trapezoid samples per piece) other than the default 16: block
+    boundaries of the 6-sample register blocks, a single sample pair, and more samples than the latency mapping has flag
+    bits for (kappa > 31: MINCOB_MAP_LATENCY falls back to the throughput mapping).  Cost and gradient against the oracle
+    (1e-9), and the two mappings bit-identical on a short optimisation."""
+    pb = synth.make_problems(70, N=5, K=16, S=3)
+    mb = handles[3]
+    prm = default_params(3, kappa=kappa, max_iterations=25)
+    mb.set_params(prm)
+    mb.set_problems(pb)
+    rng = np.random.default_rng(kappa)
+    x = pb.x0() + 0.05 * rng.normal(size=pb.x0().shape)
+    f, g = mb.evaluate(x)
+    fo, go = oracle.cost_batch(prm, pb, x, nthreads=8)
+    assert float(np.max(np.abs(f - fo) / np.abs(fo))) <= TOL and rel_rows(g, go) <= TOL
+    out = {}
+    for mp in (P.MAP_THROUGHPUT, P.MAP_LATENCY):
+        prm.mapping = mp
+        mb.set_params(prm)
+        out[mp] = mb.optimize(pb.x0())
+        assert mb.last_mapping() == (mp if kappa <= 31 else P.MAP_THROUGHPUT)
+    for k in ("x", "f", "status", "iters", "evals", "coeffs", "T"):
+        np.testing.assert_array_equal(out[P.MAP_THROUGHPUT][k], out[P.MAP_LATENCY][k], err_msg=k)
+    fo2, _ = oracle.cost_batch(prm, pb, out[P.MAP_LATENCY]["x"], nthreads=8)
+    assert float(np.max(np.abs(out[P.MAP_LATENCY]["f"] - fo2) / np.abs(fo2))) <= TOL
+    mb.set_params(default_params(3))
