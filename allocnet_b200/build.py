@@ -24,7 +24,7 @@ EXTRA = os.environ.get("MINCOB_EXTRA_FLAGS", "").split()
 MINB = {3: int(os.environ.get("MINCOB_MINB3", "3")), 4: int(os.environ.get("MINCOB_MINB4", "2"))}
 # threads per block per LPT: the LPT = 5 objects (six trajectories per warp) use one-warp blocks so that shared memory,
 # not the block granularity, decides how many warps fit (11 per SM at N = 5, K = 16); MINB scales to the same register cap
-THREADS = {5: int(os.environ.get("MINCOB_THREADS5", "32"))}
+THREADS = {5: int(os.environ.get("MINCOB_THREADS5", "32")), 8: int(os.environ.get("MINCOB_THREADS8", "128"))}
 
 
 def _nvcc():
